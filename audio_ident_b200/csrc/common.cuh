@@ -1,0 +1,68 @@
+// common.cuh -- shared declarations for the sm_100a fingerprint engine kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/aid_params.h"
+#include "../../include/audio_ident_b200.h"
+
+#define AID_FULL_MASK 0xffffffffu
+
+// ---- work units ------------------------------------------------------------------
+// A ragged batch is cut into fixed-size units so that every kernel's grid is a flat list
+// and a CTA (or warp) finds its unit with one lookup.
+struct aid_stft_unit {     // one warp: frames [frame0, frame0 + n_frames) of one track
+    int64_t pcm_begin;     // first sample of the track in the batch PCM buffer
+    int64_t n_samples;     // samples in the track
+    int64_t spec_row;      // row of (track, frame0) in the batch spectrogram
+    int32_t frame0;
+    int32_t n_frames;
+};
+
+struct aid_peak_unit {     // one CTA: output rows [row0, row0 + n_rows) of one track
+    int64_t spec_row0;     // row of (track, frame 0) in the batch spectrogram
+    int32_t track;         // index in the batch
+    int32_t n_frames;      // frames in the track
+    int32_t row0;
+    int32_t n_rows;
+};
+
+#define AID_STFT_UNIT_FRAMES   64      // frames per warp-unit (even)
+#define AID_PEAK_BLOCK_FRAMES  256     // must equal the spec's aligned block (aid_params.h)
+
+// ---- kernel launchers (defined in the .cu files, called by engine.cu) --------------
+struct aid_tables {              // device-resident constant tables, built once per engine
+    const float*  window;        // [1024] float32 Hamming
+    const float2* twiddle;       // [32][32] W_1024^(k1*n1), k1-major
+};
+
+cudaError_t aid_launch_stft(const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
+                            int n_units, float* d_spec, cudaStream_t st);
+
+cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, int n_units,
+                             uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
+                             cudaStream_t st);
+
+cudaError_t aid_launch_peak_compact(const uint32_t* d_slots, const uint32_t* d_unit_count,
+                                    const uint32_t* d_unit_pos, const aid_peak_unit* d_units, int n_units,
+                                    uint32_t* d_peaks, uint32_t* d_peak_track, cudaStream_t st);
+
+// exclusive scan of n uint32 values, in place is allowed (out == in); d_tmp holds
+// aid_scan_tmp_elems(n) uint32; the grand total is also written to *d_total if non-null.
+// If d_n is non-null only the first min(n, *d_n + 1) values are scanned (length known on the device).
+size_t aid_scan_tmp_elems(int64_t n);
+cudaError_t aid_launch_scan_u32(const uint32_t* d_in, uint32_t* d_out, int64_t n, uint32_t* d_tmp,
+                                uint32_t* d_total, const uint32_t* d_n, cudaStream_t st);
+
+cudaError_t aid_launch_hash_count(const uint32_t* d_peaks, const uint32_t* d_peak_track,
+                                  const uint32_t* d_peak_off, const uint32_t* d_n_peaks_total,
+                                  int64_t max_peaks, uint32_t* d_cnt, cudaStream_t st);
+cudaError_t aid_launch_hash_write(const uint32_t* d_peaks, const uint32_t* d_peak_track,
+                                  const uint32_t* d_peak_off, const uint32_t* d_n_peaks_total,
+                                  int64_t max_peaks, const uint32_t* d_pos,
+                                  uint32_t* d_hash, uint32_t* d_t, int64_t hash_cap, int32_t* d_overflow,
+                                  cudaStream_t st);
+
+cudaError_t aid_launch_gather_u32(const uint32_t* d_src, const uint32_t* d_idx, uint32_t* d_dst, int n,
+                                  cudaStream_t st);
+cudaError_t aid_launch_synth(float* d_pcm, int64_t first_track, int n_tracks, int64_t samples_per_track,
+                             uint64_t seed, cudaStream_t st);

@@ -1,0 +1,461 @@
+// index.cu -- the hash index resident in HBM: segments, build (counting sort by hash), persistence.
+//
+// Replaces stage a7/a8 of SURVEY.md section 8(a): the LMDB store behind `olaf_c store` / `olaf_c del`
+// (reference audio-ident-service/app/audio/fingerprint.py:117-125, :239-246; directory = settings.olaf_lmdb_path,
+// fingerprint.py:79-84). Definition of the sorted order: oracle/aid_oracle.c aid_oracle_index_build().
+//
+// Layout (DESIGN.md "Index"): the index is a list of segments of at most AID_SEG_TRACKS (16384) tracks.
+// A segment keeps
+//   entries  : (hash u32, posting u32) in arrival order, posting = (local_track << 18) | t_anchor
+//   bucket   : u32[2^24 + 1], bucket[h] = first sorted posting of hash h
+//   postings : u32[n], ordered by (hash, local_track, t_anchor)
+// Build = histogram over hashes (global atomics) -> exclusive scan (the bucket table itself) -> scatter with
+// per-bucket cursors -> per-bucket sort (buckets hold a handful of postings). Only the last segment is open;
+// adding tracks marks it dirty and the next query (or aid_index_commit) rebuilds just that segment.
+// Deleting a track sets a tombstone bit that the matcher checks; its postings stay until the segment is rebuilt.
+#include <errno.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include "engine.h"
+#include "index.h"
+
+namespace {
+
+constexpr int64_t kBuckets = (int64_t)1 << AID_HASH_BITS;
+
+// one CTA per track of the sub-batch: copy its hashes into the segment's entry arrays
+struct AppendJob { const uint32_t* src_hash; const uint32_t* src_t; uint32_t* dst_hash; uint32_t* dst_post; uint32_t n; uint32_t local; };
+
+__global__ void k_append(const AppendJob* __restrict__ jobs) {
+    const AppendJob j = jobs[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < j.n; i += blockDim.x) {
+        j.dst_hash[i] = j.src_hash[i];
+        j.dst_post[i] = (j.local << AID_POST_T_BITS) | j.src_t[i];
+    }
+}
+
+__global__ void k_hist(const uint32_t* __restrict__ hash, int64_t n, uint32_t* __restrict__ bucket) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(bucket + hash[i], 1u);
+}
+
+__global__ void k_scatter(const uint32_t* __restrict__ hash, const uint32_t* __restrict__ post, int64_t n,
+                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ postings) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        postings[atomicAdd(cursor + hash[i], 1u)] = post[i];
+}
+
+// ascending sort of every bucket (one thread per bucket; buckets average a few postings)
+__global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, uint32_t* __restrict__ postings) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= kBuckets) return;
+    const uint32_t b = bucket[h], e = bucket[h + 1];
+    const uint32_t n = e - b;
+    if (n < 2) return;
+    uint32_t* a = postings + b;
+    if (n <= 32) {                                   // insertion sort
+        for (uint32_t i = 1; i < n; i++) {
+            const uint32_t v = a[i];
+            uint32_t j = i;
+            while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; j--; }
+            a[j] = v;
+        }
+        return;
+    }
+    // heapsort, in place
+    auto sift = [&](uint32_t start, uint32_t end) {
+        uint32_t root = start;
+        while (2 * root + 1 <= end) {
+            uint32_t child = 2 * root + 1, sw = root;
+            if (a[sw] < a[child]) sw = child;
+            if (child + 1 <= end && a[sw] < a[child + 1]) sw = child + 1;
+            if (sw == root) return;
+            const uint32_t t = a[root]; a[root] = a[sw]; a[sw] = t;
+            root = sw;
+        }
+    };
+    for (int64_t s = (int64_t)(n - 2) / 2; s >= 0; s--) sift((uint32_t)s, n - 1);
+    for (uint32_t end = n - 1; end > 0; end--) {
+        const uint32_t t = a[end]; a[end] = a[0]; a[0] = t;
+        sift(0, end - 1);
+    }
+}
+
+cudaError_t grow_copy(DevBuf& b, size_t used_bytes, size_t need_bytes) {
+    if (need_bytes <= b.cap) return cudaSuccess;
+    size_t want = std::max(need_bytes, b.cap * 2);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) { want = need_bytes; e = cudaMalloc(&np, want); }
+    if (e != cudaSuccess) return e;
+    if (b.p && used_bytes) e = cudaMemcpy(np, b.p, used_bytes, cudaMemcpyDeviceToDevice);
+    if (b.p) cudaFree(b.p);
+    b.p = np; b.cap = want;
+    return e;
+}
+
+}  // namespace
+
+Index* aid_index_new() { return new Index(); }
+
+void Segment::release() { st_hash.release(); st_post.release(); bucket.release(); postings.release(); tomb.release(); }
+
+void aid_index_free(aid_engine*, Index* ix) {
+    if (!ix) return;
+    for (Segment* s : ix->segs) { s->release(); delete s; }
+    ix->cursor.release(); ix->scan_tmp.release(); ix->d_jobs.release(); ix->d_segdesc.release();
+    ix->cand.release(); ix->cand_n.release(); ix->rows.release(); ix->rows_n.release();
+    delete ix;
+}
+
+static Segment* open_segment(aid_engine* e, Index* ix) {
+    if (!ix->segs.empty() && ix->segs.back()->n_tracks < AID_SEG_TRACKS) return ix->segs.back();
+    Segment* s = new Segment();
+    s->first_track = (uint32_t)ix->segs.size() * AID_SEG_TRACKS;
+    if (s->tomb.ensure(AID_SEG_TRACKS / 8) != cudaSuccess || cudaMemset(s->tomb.p, 0, AID_SEG_TRACKS / 8) != cudaSuccess) {
+        cudaGetLastError(); delete s; return nullptr;
+    }
+    s->h_tomb.assign(AID_SEG_TRACKS / 32, 0);
+    ix->segs.push_back(s);
+    ix->segdesc_dirty = true;
+    (void)e;
+    return s;
+}
+
+static int set_tombstone(aid_engine* e, Index* ix, uint32_t track) {
+    Segment* s = ix->segs[track / AID_SEG_TRACKS];
+    const uint32_t local = track % AID_SEG_TRACKS;
+    s->h_tomb[local / 32] |= 1u << (local % 32);
+    AID_CUDA(e, cudaMemcpy(s->tomb.as<uint32_t>() + local / 32, &s->h_tomb[local / 32], 4, cudaMemcpyHostToDevice));
+    TrackInfo& ti = ix->tracks[track];
+    if (!ti.deleted) { ti.deleted = true; ix->live_tracks--; }
+    return AID_OK;
+}
+
+// Registers the tracks of one fingerprinted sub-batch (results in host arrays h_off/h_status, device arrays
+// d_hash/d_t) and appends their entries to the open segment(s).
+int aid_index_append(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* h_off,
+                     const int32_t* h_status, const int64_t* n_frames, int n, const char* const* names,
+                     uint8_t* ok, cudaStream_t st) {
+    Index* ix = e->index;
+    struct Placed { Segment* seg; int64_t at; uint32_t src, cnt, local; };
+    std::vector<Placed> placed;
+    std::vector<std::pair<Segment*, int64_t>> touched;      // segment, entries it held before this call
+    placed.reserve(n);
+    for (int i = 0; i < n; i++) {
+        ok[i] = 0;
+        if (!names[i]) return AID_E_ARG;
+        const int64_t cnt = (int64_t)h_off[i + 1] - h_off[i];
+        if ((h_status[i] & (AID_TRACK_PEAK_OVERFLOW | AID_TRACK_TOO_LONG)) || n_frames[i] > AID_INDEX_MAX_FRAMES) continue;
+        if (ix->tracks.size() >= ((size_t)1 << 25)) return AID_E_FULL;
+        Segment* s = open_segment(e, ix);
+        if (!s) return aid_fail_cuda(e, cudaErrorMemoryAllocation, "segment allocation");
+        auto old = ix->by_name.find(names[i]);
+        if (old != ix->by_name.end()) { int rc = set_tombstone(e, ix, old->second); if (rc) return rc; }
+        if (touched.empty() || touched.back().first != s) touched.push_back({s, s->n_entries});
+        const uint32_t local = s->n_tracks++;
+        TrackInfo ti; ti.name = names[i]; ti.n_frames = n_frames[i]; ti.n_hashes = (uint32_t)cnt; ti.deleted = false;
+        ix->tracks.push_back(ti);
+        ix->by_name[ti.name] = s->first_track + local;
+        ix->live_tracks++;
+        if (cnt > 0) {
+            placed.push_back({s, s->n_entries, h_off[i], (uint32_t)cnt, local});
+            s->n_entries += cnt;
+            s->dirty = true;
+            ix->n_postings += cnt;
+        }
+        ok[i] = 1;
+    }
+    for (auto& t : touched) {
+        AID_CUDA(e, grow_copy(t.first->st_hash, (size_t)t.second * 4, (size_t)t.first->n_entries * 4));
+        AID_CUDA(e, grow_copy(t.first->st_post, (size_t)t.second * 4, (size_t)t.first->n_entries * 4));
+    }
+    if (!placed.empty()) {
+        std::vector<AppendJob> jobs(placed.size());
+        for (size_t k = 0; k < placed.size(); k++) {
+            const Placed& p = placed[k];
+            jobs[k].src_hash = d_hash + p.src; jobs[k].src_t = d_t + p.src;
+            jobs[k].dst_hash = p.seg->st_hash.as<uint32_t>() + p.at; jobs[k].dst_post = p.seg->st_post.as<uint32_t>() + p.at;
+            jobs[k].n = p.cnt; jobs[k].local = p.local;
+        }
+        AID_CUDA(e, ix->d_jobs.ensure(jobs.size() * sizeof(AppendJob)));
+        AID_CUDA(e, cudaMemcpyAsync(ix->d_jobs.p, jobs.data(), jobs.size() * sizeof(AppendJob), cudaMemcpyHostToDevice, st));
+        k_append<<<(unsigned)jobs.size(), 128, 0, st>>>(ix->d_jobs.as<AppendJob>());
+        AID_CUDA(e, cudaGetLastError());
+        AID_CUDA(e, cudaStreamSynchronize(st));
+        e->launches += 1;
+    }
+    return AID_OK;
+}
+
+static int build_segment(aid_engine* e, Index* ix, Segment* s, cudaStream_t st) {
+    const int64_t n = s->n_entries;
+    AID_CUDA(e, s->bucket.ensure((size_t)(kBuckets + 1) * 4));
+    AID_CUDA(e, ix->cursor.ensure((size_t)(kBuckets + 1) * 4));
+    AID_CUDA(e, ix->scan_tmp.ensure(aid_scan_tmp_elems(kBuckets + 1) * 4));
+    AID_CUDA(e, s->postings.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    uint32_t* bucket = s->bucket.as<uint32_t>();
+    AID_CUDA(e, cudaMemsetAsync(bucket, 0, (size_t)(kBuckets + 1) * 4, st));
+    if (n > 0) {
+        const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+        k_hist<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), n, bucket);
+        AID_CUDA(e, aid_launch_scan_u32(bucket, bucket, kBuckets + 1, ix->scan_tmp.as<uint32_t>(), nullptr, nullptr, st));
+        AID_CUDA(e, cudaMemcpyAsync(ix->cursor.p, bucket, (size_t)(kBuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        k_scatter<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), s->st_post.as<uint32_t>(), n, ix->cursor.as<uint32_t>(),
+                                        s->postings.as<uint32_t>());
+        k_bucket_sort<<<(unsigned)((kBuckets + 255) / 256), 256, 0, st>>>(bucket, s->postings.as<uint32_t>());
+        AID_CUDA(e, cudaGetLastError());
+        e->launches += 6;
+    }
+    s->dirty = false;
+    ix->segdesc_dirty = true;
+    return AID_OK;
+}
+
+int aid_index_commit_on(aid_engine* e, cudaStream_t st) {
+    Index* ix = e->index;
+    for (Segment* s : ix->segs)
+        if (s->dirty || (!s->bucket.p)) { int rc = build_segment(e, ix, s, st); if (rc) return rc; }
+    if (ix->segdesc_dirty) {
+        std::vector<aid_seg_desc> d(ix->segs.size());
+        for (size_t i = 0; i < d.size(); i++) {
+            d[i].bucket = ix->segs[i]->bucket.as<uint32_t>();
+            d[i].postings = ix->segs[i]->postings.as<uint32_t>();
+            d[i].tomb = ix->segs[i]->tomb.as<uint32_t>();
+            d[i].first_track = ix->segs[i]->first_track;
+            d[i].n_tracks = ix->segs[i]->n_tracks;
+        }
+        AID_CUDA(e, ix->d_segdesc.ensure(std::max<size_t>(d.size(), 1) * sizeof(aid_seg_desc)));
+        AID_CUDA(e, cudaStreamSynchronize(st));
+        if (!d.empty()) AID_CUDA(e, cudaMemcpy(ix->d_segdesc.p, d.data(), d.size() * sizeof(aid_seg_desc), cudaMemcpyHostToDevice));
+        ix->segdesc_dirty = false;
+    }
+    return AID_OK;
+}
+
+// ----------------------------------------------------------------------------------------- C ABI
+static int add_pcm(aid_engine* e, const float* pcm, bool on_device, const int64_t* sample_off, int n_tracks,
+                   const char* const* names, uint8_t* ok) {
+    if (!e || !sample_off || !names || !ok || n_tracks < 0) return AID_E_ARG;
+    if (n_tracks > 0 && !pcm && sample_off[n_tracks] > sample_off[0]) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Slot& s = e->slot[0];
+    for (int first = 0; first < n_tracks;) {
+        int64_t frames = 0; int count = 0;
+        while (first + count < n_tracks) {
+            const int64_t T = aid_num_frames(sample_off[first + count + 1] - sample_off[first + count]);
+            if (count > 0 && frames + T > e->max_batch_frames) break;
+            frames += T; count++;
+        }
+        Plan plan;
+        int rc = aid_build_plan(sample_off, first, count, AID_INDEX_MAX_FRAMES, plan);
+        if (rc) return rc;
+        const int64_t samples = sample_off[first + count] - sample_off[first];
+        if ((rc = aid_slot_prepare(e, s, plan, !on_device, samples))) return rc;
+        const float* d_pcm = pcm + sample_off[first];
+        if (!on_device) {
+            if (samples > 0) AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + sample_off[first], (size_t)samples * 4, cudaMemcpyHostToDevice, s.st));
+            d_pcm = s.pcm.as<float>();
+        }
+        if ((rc = aid_run_fingerprint(e, s, plan, d_pcm, s.st))) return rc;
+        std::vector<uint32_t> h_off(count + 1);
+        std::vector<int32_t> h_st(count);
+        AID_CUDA(e, cudaMemcpyAsync(h_off.data(), s.hash_off.p, (size_t)(count + 1) * 4, cudaMemcpyDeviceToHost, s.st));
+        AID_CUDA(e, cudaMemcpyAsync(h_st.data(), s.status.p, (size_t)count * 4, cudaMemcpyDeviceToHost, s.st));
+        AID_CUDA(e, cudaStreamSynchronize(s.st));
+        for (int i = 0; i < count; i++) h_st[i] |= plan.host_status[i];
+        // frames of too-long tracks were planned as 0; report their true length so they are refused
+        std::vector<int64_t> nf(count);
+        for (int i = 0; i < count; i++) nf[i] = aid_num_frames(sample_off[first + i + 1] - sample_off[first + i]);
+        if ((rc = aid_index_append(e, s.hash.as<uint32_t>(), s.t.as<uint32_t>(), h_off.data(), h_st.data(), nf.data(),
+                                   count, names + first, ok + first, s.st))) return rc;
+        first += count;
+    }
+    return AID_OK;
+}
+
+extern "C" int aid_index_add_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
+                                  const char* const* names, uint8_t* ok) {
+    return add_pcm(e, pcm, false, sample_off, n_tracks, names, ok);
+}
+extern "C" int aid_index_add_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_tracks,
+                                 const char* const* names, uint8_t* ok) {
+    return add_pcm(e, d_pcm, true, sample_off, n_tracks, names, ok);
+}
+
+extern "C" int aid_index_add_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anchor,
+                                    const int64_t* hash_off, const int64_t* n_frames, int n_tracks,
+                                    const char* const* names, uint8_t* ok) {
+    if (!e || !hash_off || !n_frames || !names || !ok || n_tracks < 0) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Slot& s = e->slot[0];
+    const int chunk = 4096;
+    for (int first = 0; first < n_tracks; first += chunk) {
+        const int count = std::min(chunk, n_tracks - first);
+        const int64_t h0 = hash_off[first], total = hash_off[first + count] - h0;
+        if (total < 0 || total >= ((int64_t)1 << 32)) return AID_E_ARG;
+        if (total > 0 && (!hash || !t_anchor)) return AID_E_ARG;
+        AID_CUDA(e, s.hash.ensure((size_t)std::max<int64_t>(total, 1) * 4));
+        AID_CUDA(e, s.t.ensure((size_t)std::max<int64_t>(total, 1) * 4));
+        if (total > 0) {
+            AID_CUDA(e, cudaMemcpyAsync(s.hash.p, hash + h0, (size_t)total * 4, cudaMemcpyHostToDevice, s.st));
+            AID_CUDA(e, cudaMemcpyAsync(s.t.p, t_anchor + h0, (size_t)total * 4, cudaMemcpyHostToDevice, s.st));
+        }
+        std::vector<uint32_t> h_off(count + 1);
+        std::vector<int32_t> h_st(count, 0);
+        for (int i = 0; i <= count; i++) {
+            if (hash_off[first + i] < h0) return AID_E_ARG;
+            h_off[i] = (uint32_t)(hash_off[first + i] - h0);
+        }
+        int rc = aid_index_append(e, s.hash.as<uint32_t>(), s.t.as<uint32_t>(), h_off.data(), h_st.data(), n_frames + first,
+                                  count, names + first, ok + first, s.st);
+        if (rc) return rc;
+    }
+    return AID_OK;
+}
+
+extern "C" int aid_index_delete(aid_engine* e, const char* name) {
+    if (!e || !name) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Index* ix = e->index;
+    auto it = ix->by_name.find(name);
+    if (it == ix->by_name.end()) return AID_E_NOT_FOUND;
+    const uint32_t track = it->second;
+    ix->by_name.erase(it);
+    return set_tombstone(e, ix, track);
+}
+
+extern "C" int aid_index_commit(aid_engine* e) {
+    if (!e) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    int rc = aid_index_commit_on(e, e->slot[0].st);
+    if (rc) return rc;
+    AID_CUDA(e, cudaStreamSynchronize(e->slot[0].st));
+    return AID_OK;
+}
+
+extern "C" int aid_index_clear(aid_engine* e) {
+    if (!e) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    AID_CUDA(e, cudaDeviceSynchronize());
+    aid_index_free(e, e->index);
+    e->index = aid_index_new();
+    return AID_OK;
+}
+
+extern "C" int aid_index_stats(aid_engine* e, int64_t* out) {
+    if (!e || !out) return AID_E_ARG;
+    Index* ix = e->index;
+    out[0] = ix->live_tracks; out[1] = ix->n_postings; out[2] = (int64_t)ix->segs.size(); out[3] = (int64_t)ix->tracks.size();
+    int64_t bytes = (int64_t)ix->cursor.cap + ix->scan_tmp.cap;
+    for (Segment* s : ix->segs) bytes += s->st_hash.cap + s->st_post.cap + s->bucket.cap + s->postings.cap + s->tomb.cap;
+    out[4] = bytes;
+    return AID_OK;
+}
+
+extern "C" int aid_index_track_name(aid_engine* e, uint32_t track, char* buf, int buf_len) {
+    if (!e || !buf || buf_len < 1) return AID_E_ARG;
+    Index* ix = e->index;
+    if (track >= ix->tracks.size()) return AID_E_NOT_FOUND;
+    const std::string& s = ix->tracks[track].name;
+    if ((int)s.size() + 1 > buf_len) return AID_E_CAPACITY;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+// ------------------------------------------------------------------------------------ persistence
+// One file, <dir>/aidx_b200.bin: header, track table, then per segment its (hash, posting) entries.
+// The sorted form is rebuilt on load. Written to a temp name and renamed, so a crash leaves the old file.
+namespace {
+struct FileHeader { char magic[8]; uint32_t version, n_segments; uint64_t n_tracks, n_postings; };
+const char kMagic[8] = {'A', 'I', 'D', 'X', 'B', '2', '0', '0'};
+bool wr(FILE* f, const void* p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+bool rd(FILE* f, void* p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+}
+
+extern "C" int aid_index_save(aid_engine* e, const char* dir) {
+    if (!e || !dir) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    AID_CUDA(e, cudaDeviceSynchronize());
+    Index* ix = e->index;
+    mkdir(dir, 0777);
+    const std::string tmp = std::string(dir) + "/aidx_b200.bin.tmp", fin = std::string(dir) + "/aidx_b200.bin";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { e->err = std::string("cannot write ") + tmp + ": " + strerror(errno); return AID_E_IO; }
+    FileHeader h; memcpy(h.magic, kMagic, 8); h.version = 1; h.n_segments = (uint32_t)ix->segs.size();
+    h.n_tracks = ix->tracks.size(); h.n_postings = (uint64_t)ix->n_postings;
+    bool good = wr(f, &h, sizeof h);
+    for (const TrackInfo& t : ix->tracks) {
+        const uint32_t len = (uint32_t)t.name.size(); const uint8_t del = t.deleted;
+        good = good && wr(f, &len, 4) && wr(f, t.name.data(), len) && wr(f, &t.n_frames, 8) && wr(f, &t.n_hashes, 4) && wr(f, &del, 1);
+    }
+    std::vector<uint32_t> buf;
+    for (Segment* s : ix->segs) {
+        const uint64_t n = (uint64_t)s->n_entries; const uint32_t nt = s->n_tracks;
+        good = good && wr(f, &nt, 4) && wr(f, &n, 8);
+        buf.resize((size_t)n);
+        for (DevBuf* src : {&s->st_hash, &s->st_post}) {
+            if (n && cudaMemcpy(buf.data(), src->p, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); return aid_fail_cuda(e, cudaGetLastError(), "save D2H"); }
+            good = good && wr(f, buf.data(), (size_t)n * 4);
+        }
+    }
+    good = (fclose(f) == 0) && good;
+    if (!good || rename(tmp.c_str(), fin.c_str()) != 0) { e->err = std::string("cannot write ") + fin + ": " + strerror(errno); remove(tmp.c_str()); return AID_E_IO; }
+    return AID_OK;
+}
+
+extern "C" int aid_index_load(aid_engine* e, const char* dir) {
+    if (!e || !dir) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    const std::string fin = std::string(dir) + "/aidx_b200.bin";
+    FILE* f = fopen(fin.c_str(), "rb");
+    if (!f) {
+        if (errno == ENOENT) return aid_index_clear(e);          // emptied directory == empty index (Makefile:84-93)
+        e->err = std::string("cannot read ") + fin + ": " + strerror(errno);
+        return AID_E_IO;
+    }
+    FileHeader h;
+    if (!rd(f, &h, sizeof h) || memcmp(h.magic, kMagic, 8) != 0 || h.version != 1) { fclose(f); return AID_E_FORMAT; }
+    int rc = aid_index_clear(e);
+    if (rc) { fclose(f); return rc; }
+    Index* ix = e->index;
+    bool good = true;
+    ix->tracks.resize((size_t)h.n_tracks);
+    for (size_t i = 0; i < ix->tracks.size() && good; i++) {
+        uint32_t len = 0; uint8_t del = 0; TrackInfo& t = ix->tracks[i];
+        good = rd(f, &len, 4) && len < 4096;
+        if (!good) break;
+        t.name.resize(len);
+        good = rd(f, &t.name[0], len) && rd(f, &t.n_frames, 8) && rd(f, &t.n_hashes, 4) && rd(f, &del, 1);
+        t.deleted = del != 0;
+        if (!t.deleted) { ix->by_name[t.name] = (uint32_t)i; ix->live_tracks++; }
+    }
+    std::vector<uint32_t> buf;
+    for (uint32_t si = 0; si < h.n_segments && good; si++) {
+        uint32_t nt = 0; uint64_t n = 0;
+        good = rd(f, &nt, 4) && rd(f, &n, 8) && nt <= AID_SEG_TRACKS;
+        if (!good) break;
+        Segment* s = new Segment();
+        s->first_track = si * AID_SEG_TRACKS; s->n_tracks = nt; s->n_entries = (int64_t)n; s->dirty = true;
+        s->h_tomb.assign(AID_SEG_TRACKS / 32, 0);
+        ix->segs.push_back(s);
+        for (uint32_t l = 0; l < nt; l++)
+            if (s->first_track + l < ix->tracks.size() && ix->tracks[s->first_track + l].deleted) s->h_tomb[l / 32] |= 1u << (l % 32);
+        cudaError_t ce = s->tomb.ensure(AID_SEG_TRACKS / 8);
+        if (ce == cudaSuccess) ce = cudaMemcpy(s->tomb.p, s->h_tomb.data(), AID_SEG_TRACKS / 8, cudaMemcpyHostToDevice);
+        buf.resize((size_t)n);
+        for (DevBuf* dst : {&s->st_hash, &s->st_post}) {
+            good = good && rd(f, buf.data(), (size_t)n * 4);
+            if (ce == cudaSuccess) ce = dst->ensure(std::max<size_t>((size_t)n, 1) * 4);
+            if (ce == cudaSuccess && n && good) ce = cudaMemcpy(dst->p, buf.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+        }
+        if (ce != cudaSuccess) { fclose(f); aid_index_clear(e); return aid_fail_cuda(e, ce, "load H2D"); }
+        ix->n_postings += (int64_t)n;
+    }
+    fclose(f);
+    if (!good) { aid_index_clear(e); return AID_E_FORMAT; }
+    ix->segdesc_dirty = true;
+    return aid_index_commit(e);
+}

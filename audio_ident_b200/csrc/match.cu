@@ -1,0 +1,380 @@
+// match.cu -- hash-index probe + per-track time-offset histogram vote + top-k, sm_100a.
+//
+// Replaces stage a9 of SURVEY.md section 8(a): the lookup and tally inside `olaf_c query`
+// (reference audio-ident-service/app/audio/fingerprint.py:185-193); rows carry what one CSV line of its
+// output carries (fingerprint.py:273-277). Definition of the result: oracle/aid_oracle.c aid_oracle_match();
+// bit-exact rows (count, track, offset, q_first, q_last) in the same order.
+//
+// k_match: one CTA per (query window, index segment).
+//   0. stage the query's hashes: bucket begin / length per hash, prefix sum of the lengths -> a flat list of
+//      votes, so every thread handles the same number of postings whatever the bucket sizes are;
+//   1. pass 1 adds every vote key (local_track << 18 | t_ref - t_query + bias: one integer add on the posting)
+//      into a 4096-counter shared-memory sketch with atomics;
+//   2. pass 2 re-reads the postings (now in L2) and inserts only keys whose sketch counter reached
+//      AID_MIN_VOTES into an exact shared-memory hash table (atomicCAS on the key, atomicAdd on the count,
+//      atomicMin/Max on the query time);
+//   3. exact counts >= AID_MIN_VOTES are merged into the CTA's running top-50 with a bitonic network.
+//   Windows with more votes than the sketch can filter are processed in R rounds over a hash partition of
+//   the keys; if the exact table still fills up the CTA doubles R and starts over. Exactness never depends on
+//   the sketch: it only rejects keys that cannot reach the threshold.
+// k_rank: one CTA per query merges the per-segment top-50 lists (a track lives in exactly one segment, so no
+//   partial counts ever need adding) and writes the final rows.
+// HBM traffic per query window: 8 B of bucket table per hash and 4 B per posting touched, random access.
+#include <algorithm>
+#include "engine.h"
+#include "index.h"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kSketch = 4096;
+constexpr int kTable = 256;
+constexpr int kTableMaxLoad = 192;
+constexpr int kQChunk = 512;
+constexpr int kVotesPerRound = 2048;
+constexpr int kBest = 64;                 // >= AID_MAX_ROWS, power of two
+constexpr int kSortN = 512;               // kTable + kBest <= kSortN
+constexpr uint32_t kEmpty = 0xffffffffu;
+constexpr uint64_t kPad = ~0ull;
+
+struct CandEntry { uint32_t inv_count; uint32_t key; uint32_t tq; };   // tq = q_first | q_last << 16
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+
+template <int N, int T>
+__device__ __forceinline__ void bitonic_sort(uint64_t* key, uint32_t* val, int tid) {
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < N; i += T) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint64_t a = key[i], b = key[p];
+                    if ((a > b) == ((i & k) == 0)) {
+                        key[i] = b; key[p] = a;
+                        const uint32_t t = val[i]; val[i] = val[p]; val[p] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+struct MatchSmem {
+    uint32_t sketch[kSketch];
+    uint32_t tkey[kTable], tcnt[kTable], tmin[kTable], tmax[kTable];
+    uint32_t qbeg[kQChunk], qadd[kQChunk], qstart[kQChunk + 1];
+    uint64_t skey[kSortN];
+    uint32_t sval[kSortN];
+    uint64_t bkey[kBest];
+    uint32_t bval[kBest];
+    uint32_t wsum[kThreads / 32];
+    uint32_t total, used, overflow, nbest;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, const uint32_t* __restrict__ hash_off,
+        const int32_t* __restrict__ q_status, const aid_seg_desc* __restrict__ segs, int n_seg,
+        CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n) {
+    __shared__ MatchSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x / n_seg, sg = blockIdx.x % n_seg;
+    const aid_seg_desc seg = segs[sg];
+    const uint32_t h0 = hash_off[q];
+    const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : hash_off[q + 1] - h0;
+    const uint32_t* __restrict__ bucket = seg.bucket;
+    const uint32_t* __restrict__ postings = seg.postings;
+
+    // ---- how many votes does this (window, segment) produce?
+    uint32_t mine = 0;
+    for (uint32_t i = tid; i < nh; i += kThreads) {
+        const uint32_t h = q_hash[h0 + i];
+        mine += bucket[h + 1] - bucket[h];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(AID_FULL_MASK, mine, d);
+    if (lane == 0) sm.wsum[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kThreads / 32; w++) t += sm.wsum[w];
+        sm.total = t;
+    }
+    __syncthreads();
+    const uint32_t total = sm.total;
+    if (total < AID_MIN_VOTES) {
+        if (tid == 0) cand_n[blockIdx.x] = 0;
+        return;
+    }
+    uint32_t R = (total + kVotesPerRound - 1) / kVotesPerRound;
+
+    for (;;) {                                        // restarted with a finer partition if the exact table fills
+        if (tid == 0) { sm.nbest = 0; sm.overflow = 0; }
+        for (uint32_t r = 0; r < R; r++) {
+            for (int i = tid; i < kSketch; i += kThreads) sm.sketch[i] = 0;
+            for (int i = tid; i < kTable; i += kThreads) { sm.tkey[i] = kEmpty; sm.tcnt[i] = 0; sm.tmin[i] = 0xffffffffu; sm.tmax[i] = 0; }
+            if (tid == 0) sm.used = 0;
+            __syncthreads();
+            for (int pass = 0; pass < 2; pass++) {
+                for (uint32_t c0 = 0; c0 < nh; c0 += kQChunk) {
+                    const uint32_t nc = min((uint32_t)kQChunk, nh - c0);
+                    // stage the chunk: bucket begin, length prefix, time bias
+                    uint32_t run = 0;           // votes of earlier strides of this chunk
+                    for (uint32_t b = 0; b < nc; b += kThreads) {
+                        const uint32_t i = b + tid;
+                        uint32_t len = 0;
+                        if (i < nc) {
+                            const uint32_t h = q_hash[h0 + c0 + i];
+                            const uint32_t lo = bucket[h];
+                            len = bucket[h + 1] - lo;
+                            sm.qbeg[i] = lo;
+                            sm.qadd[i] = AID_QUERY_MAX_FRAMES - q_t[h0 + c0 + i];
+                        }
+                        uint32_t incl = len;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t o = __shfl_up_sync(AID_FULL_MASK, incl, d);
+                            if (lane >= d) incl += o;
+                        }
+                        if (lane == 31) sm.wsum[warp] = incl;
+                        __syncthreads();
+                        uint32_t before = 0, all = 0;
+#pragma unroll
+                        for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = sm.wsum[w]; all += c; before += w < warp ? c : 0; }
+                        if (i < nc) sm.qstart[i] = run + before + incl - len;
+                        run += all;
+                        __syncthreads();
+                    }
+                    if (tid == 0) sm.qstart[nc] = run;
+                    __syncthreads();
+                    const uint32_t nv = run;
+                    for (uint32_t v = tid; v < nv; v += kThreads) {
+                        // largest i with qstart[i] <= v
+                        uint32_t lo = 0, hi = nc;
+                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; }
+                        const uint32_t post = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
+                        const uint32_t local = post >> AID_POST_T_BITS;
+                        if (seg.tomb[local >> 5] & (1u << (local & 31))) continue;
+                        const uint32_t key = post + sm.qadd[lo];
+                        const uint32_t m = mix32(key);
+                        if (R > 1 && (m >> 12) % R != r) continue;
+                        const uint32_t idx = m & (kSketch - 1);
+                        if (pass == 0) { atomicAdd(&sm.sketch[idx], 1u); continue; }
+                        if (sm.sketch[idx] < AID_MIN_VOTES) continue;
+                        const uint32_t tq = AID_QUERY_MAX_FRAMES - sm.qadd[lo];
+                        uint32_t slot = (m >> 20) & (kTable - 1);
+                        for (int probe = 0; probe < kTable; probe++) {
+                            const uint32_t old = atomicCAS(&sm.tkey[slot], kEmpty, key);
+                            if (old == kEmpty) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
+                            if (old == kEmpty || old == key) {
+                                atomicAdd(&sm.tcnt[slot], 1u);
+                                atomicMin(&sm.tmin[slot], tq);
+                                atomicMax(&sm.tmax[slot], tq);
+                                break;
+                            }
+                            slot = (slot + 1) & (kTable - 1);
+                            if (probe == kTable - 1) sm.overflow = 1;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (sm.overflow) break;
+            // ---- merge this round's exact counts into the running top-kBest
+            const uint32_t nb = sm.nbest;
+            for (int i = tid; i < kSortN; i += kThreads) {
+                uint64_t k = kPad; uint32_t v = 0;
+                if (i < kTable) {
+                    if (sm.tkey[i] != kEmpty && sm.tcnt[i] >= AID_MIN_VOTES) {
+                        k = ((uint64_t)(0xffffffffu - sm.tcnt[i]) << 32) | sm.tkey[i];
+                        v = (sm.tmin[i] & 0xffffu) | (sm.tmax[i] << 16);
+                    }
+                } else if (i - kTable < (int)nb) { k = sm.bkey[i - kTable]; v = sm.bval[i - kTable]; }
+                sm.skey[i] = k; sm.sval[i] = v;
+            }
+            __syncthreads();
+            bitonic_sort<kSortN, kThreads>(sm.skey, sm.sval, tid);
+            if (tid < kBest) { sm.bkey[tid] = sm.skey[tid]; sm.bval[tid] = sm.sval[tid]; }
+            if (tid == 0) {
+                uint32_t n = 0;
+                while (n < kBest && sm.skey[n] != kPad) n++;
+                sm.nbest = n;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (!sm.overflow) break;
+        __syncthreads();
+        R *= 2;
+    }
+
+    const uint32_t n = min(sm.nbest, (uint32_t)AID_MAX_ROWS);
+    CandEntry* out = cand + (int64_t)blockIdx.x * AID_MAX_ROWS;
+    if (tid < (int)n) {
+        CandEntry c;
+        c.inv_count = (uint32_t)(sm.bkey[tid] >> 32);
+        c.key = (uint32_t)sm.bkey[tid];
+        c.tq = sm.bval[tid];
+        out[tid] = c;
+    }
+    if (tid == 0) cand_n[blockIdx.x] = n;
+}
+
+// ---- per query: merge the segments' lists, order by (count desc, track asc, offset asc), write rows
+constexpr int kRankN = 1024;
+
+__global__ void __launch_bounds__(kThreads)
+k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, const aid_seg_desc* __restrict__ segs,
+       int n_seg, int max_rows, aid_match_row* __restrict__ rows, int32_t* __restrict__ n_rows) {
+    __shared__ uint64_t skey[kRankN];
+    __shared__ uint32_t sval[kRankN];       // index of the entry in cand
+    __shared__ uint32_t s_fill, s_best;
+    const int tid = threadIdx.x, q = blockIdx.x;
+    if (tid == 0) s_best = 0;
+    __syncthreads();
+    int sg = 0;
+    while (sg < n_seg) {
+        // keep the best kBest so far in slots [0, kBest), fill the rest from the next segments
+        const uint32_t nbest = s_best;
+        for (int i = tid; i < kRankN; i += kThreads) if (i >= (int)nbest) { skey[i] = kPad; sval[i] = 0; }
+        if (tid == 0) s_fill = nbest;
+        __syncthreads();
+        while (sg < n_seg) {
+            const uint32_t n = cand_n[(int64_t)q * n_seg + sg];
+            if (s_fill + n > kRankN) break;
+            const uint32_t base = s_fill;
+            if (tid < (int)n) {
+                const int64_t ci = ((int64_t)q * n_seg + sg) * AID_MAX_ROWS + tid;
+                const CandEntry c = cand[ci];
+                const uint64_t inv = c.inv_count - (0xffffffffu - 0xfffffu);          // 20-bit inverted count
+                const uint64_t track = (uint64_t)segs[sg].first_track + (c.key >> AID_POST_T_BITS);
+                const uint64_t off = c.key & ((1u << AID_POST_T_BITS) - 1);
+                skey[base + tid] = ((c.inv_count <= 0xffffffffu - 0xfffffu ? 0ull : inv) << 44) | (track << 19) | off;
+                sval[base + tid] = (uint32_t)ci;
+            }
+            __syncthreads();
+            if (tid == 0) s_fill = base + n;
+            __syncthreads();
+            sg++;
+        }
+        bitonic_sort<kRankN, kThreads>(skey, sval, tid);
+        if (tid == 0) {
+            uint32_t n = 0;
+            while (n < kBest && skey[n] != kPad) n++;
+            s_best = n;
+        }
+        __syncthreads();
+    }
+    const uint32_t n = min(s_best, (uint32_t)max_rows);
+    if (tid < (int)n) {
+        const CandEntry c = cand[sval[tid]];
+        const uint32_t sgi = (uint32_t)((sval[tid] / AID_MAX_ROWS) % n_seg);
+        aid_match_row r;
+        r.count = (int32_t)(0xffffffffu - c.inv_count);
+        r.track = segs[sgi].first_track + (c.key >> AID_POST_T_BITS);
+        r.offset = (int32_t)(c.key & ((1u << AID_POST_T_BITS) - 1)) - AID_QUERY_MAX_FRAMES;
+        r.q_first = (int32_t)(c.tq & 0xffffu);
+        r.q_last = (int32_t)(c.tq >> 16);
+        rows[(int64_t)q * max_rows + tid] = r;
+    }
+    if (tid == 0) n_rows[q] = (int32_t)n;
+}
+
+}  // namespace
+
+// Runs the matcher for n_q windows whose fingerprints are on the device (dense, hash_off u32[n_q+1]).
+static int match_device(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
+                        const int32_t* d_status, int n_q, aid_match_row* rows, int max_rows, int32_t* n_rows,
+                        cudaStream_t st) {
+    Index* ix = e->index;
+    int rc = aid_index_commit_on(e, st);
+    if (rc) return rc;
+    const int n_seg = (int)ix->segs.size();
+    if (n_seg == 0 || n_q == 0) { for (int i = 0; i < n_q; i++) n_rows[i] = 0; return AID_OK; }
+    const int64_t n_cta = (int64_t)n_q * n_seg;
+    if (n_cta >= ((int64_t)1 << 31)) return AID_E_ARG;
+    AID_CUDA(e, ix->cand.ensure((size_t)n_cta * AID_MAX_ROWS * sizeof(CandEntry)));
+    AID_CUDA(e, ix->cand_n.ensure((size_t)n_cta * 4));
+    AID_CUDA(e, ix->rows.ensure((size_t)n_q * max_rows * sizeof(aid_match_row)));
+    AID_CUDA(e, ix->rows_n.ensure((size_t)n_q * 4));
+    k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
+                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>());
+    k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
+                                     max_rows, ix->rows.as<aid_match_row>(), ix->rows_n.as<int32_t>());
+    AID_CUDA(e, cudaGetLastError());
+    e->launches += 2;
+    AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.p, (size_t)n_q * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, st));
+    AID_CUDA(e, cudaMemcpyAsync(n_rows, ix->rows_n.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    AID_CUDA(e, cudaStreamSynchronize(st));
+    return AID_OK;
+}
+
+static int query_pcm(aid_engine* e, const float* pcm, bool on_device, const int64_t* sample_off, int n_q,
+                     aid_match_row* rows, int max_rows, int32_t* n_rows) {
+    if (!e || !sample_off || !rows || !n_rows || n_q < 0 || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
+    if (n_q > 0 && !pcm && sample_off[n_q] > sample_off[0]) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    for (int i = 0; i < n_q; i++)
+        if (aid_num_frames(sample_off[i + 1] - sample_off[i]) > AID_QUERY_MAX_FRAMES) return AID_E_TOO_LONG;
+    Slot& s = e->slot[0];
+    for (int first = 0; first < n_q;) {
+        int64_t frames = 0; int count = 0;
+        while (first + count < n_q) {
+            const int64_t T = aid_num_frames(sample_off[first + count + 1] - sample_off[first + count]);
+            if (count > 0 && frames + T > e->max_batch_frames) break;
+            frames += T; count++;
+        }
+        Plan plan;
+        int rc = aid_build_plan(sample_off, first, count, AID_QUERY_MAX_FRAMES, plan);
+        if (rc) return rc;
+        const int64_t samples = sample_off[first + count] - sample_off[first];
+        if ((rc = aid_slot_prepare(e, s, plan, !on_device, samples))) return rc;
+        const float* d_pcm = pcm + sample_off[first];
+        if (!on_device) {
+            if (samples > 0) AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + sample_off[first], (size_t)samples * 4, cudaMemcpyHostToDevice, s.st));
+            d_pcm = s.pcm.as<float>();
+        }
+        if ((rc = aid_run_fingerprint(e, s, plan, d_pcm, s.st))) return rc;
+        if ((rc = match_device(e, s.hash.as<uint32_t>(), s.t.as<uint32_t>(), s.hash_off.as<uint32_t>(), s.status.as<int32_t>(),
+                               count, rows + (int64_t)first * max_rows, max_rows, n_rows + first, s.st))) return rc;
+        first += count;
+    }
+    return AID_OK;
+}
+
+extern "C" int aid_query_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_queries,
+                              aid_match_row* rows, int max_rows, int32_t* n_rows) {
+    return query_pcm(e, pcm, false, sample_off, n_queries, rows, max_rows, n_rows);
+}
+extern "C" int aid_query_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_queries,
+                             aid_match_row* rows, int max_rows, int32_t* n_rows) {
+    return query_pcm(e, d_pcm, true, sample_off, n_queries, rows, max_rows, n_rows);
+}
+
+extern "C" int aid_query_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anchor, const int64_t* hash_off,
+                                int n_queries, aid_match_row* rows, int max_rows, int32_t* n_rows) {
+    if (!e || !hash_off || !rows || !n_rows || n_queries < 0 || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Slot& s = e->slot[0];
+    const int64_t h0 = hash_off[0], total = hash_off[n_queries] - h0;
+    if (total < 0 || total >= ((int64_t)1 << 32)) return AID_E_ARG;
+    if (total > 0 && (!hash || !t_anchor)) return AID_E_ARG;
+    std::vector<uint32_t> off32(n_queries + 1);
+    for (int i = 0; i <= n_queries; i++) {
+        if (hash_off[i] < h0 || (i && hash_off[i] < hash_off[i - 1])) return AID_E_ARG;
+        off32[i] = (uint32_t)(hash_off[i] - h0);
+    }
+    for (int64_t i = 0; i < total; i++) if (t_anchor[h0 + i] >= AID_QUERY_MAX_FRAMES || hash[h0 + i] >> AID_HASH_BITS) return AID_E_ARG;
+    AID_CUDA(e, s.hash.ensure((size_t)std::max<int64_t>(total, 1) * 4));
+    AID_CUDA(e, s.t.ensure((size_t)std::max<int64_t>(total, 1) * 4));
+    AID_CUDA(e, s.hash_off.ensure((size_t)(n_queries + 1) * 4));
+    if (total > 0) {
+        AID_CUDA(e, cudaMemcpyAsync(s.hash.p, hash + h0, (size_t)total * 4, cudaMemcpyHostToDevice, s.st));
+        AID_CUDA(e, cudaMemcpyAsync(s.t.p, t_anchor + h0, (size_t)total * 4, cudaMemcpyHostToDevice, s.st));
+    }
+    AID_CUDA(e, cudaMemcpyAsync(s.hash_off.p, off32.data(), (size_t)(n_queries + 1) * 4, cudaMemcpyHostToDevice, s.st));
+    return match_device(e, s.hash.as<uint32_t>(), s.t.as<uint32_t>(), s.hash_off.as<uint32_t>(), nullptr, n_queries, rows, max_rows,
+                        n_rows, s.st);
+}

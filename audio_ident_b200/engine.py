@@ -1,0 +1,293 @@
+"""Python view of one B200 fingerprint engine (one per process, one process per GPU).
+
+Thin by design: every method is one call into the C ABI (include/audio_ident_b200.h); numpy arrays
+are the host buffers, and anything with ``data_ptr()`` (a torch CUDA tensor) can stand in for device
+memory. There is no CPU implementation behind any of these methods.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MATCH_ROW_DTYPE, EngineUnavailable, FpDeviceResult
+
+SAMPLE_RATE = 16000
+FRAME_SECONDS = 128 / 16000
+MAX_ROWS = 50
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"audio_ident_b200: {text} (status {status})")
+        self.status = status
+
+
+def _ptr(a) -> int:
+    if a is None:
+        return 0
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    return int(a)
+
+
+def ragged(clips: Sequence) -> tuple[np.ndarray, np.ndarray]:
+    """list of float32 arrays / f32le bytes -> (concatenated float32, sample_off int64[n+1])."""
+    arrs = [np.frombuffer(c, dtype="<f4") if isinstance(c, (bytes, bytearray, memoryview))
+            else np.ascontiguousarray(c, dtype=np.float32).reshape(-1) for c in clips]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    if arrs:
+        off[1:] = np.cumsum([len(a) for a in arrs])
+    pcm = np.concatenate(arrs) if arrs else np.zeros(0, np.float32)
+    return np.ascontiguousarray(pcm, np.float32), off
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        n = self._L.aid_device_count()
+        if n <= 0:
+            raise EngineUnavailable("no CUDA device is visible; the fingerprint engine has no CPU fallback")
+        h = C.c_void_p()
+        rc = self._L.aid_engine_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EngineUnavailable(f"aid_engine_create(device={device}) failed: {self._L.aid_strerror(rc).decode()}")
+        self._h = h
+        self.device = int(device)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.aid_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            text = self._L.aid_strerror(rc).decode()
+            if rc == -1:
+                text += ": " + self._L.aid_last_error(self._h).decode()
+            raise EngineError(rc, text)
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.aid_launch_count(self._h))
+
+    def sync(self) -> None:
+        self._check(self._L.aid_engine_sync(self._h))
+
+    def set_max_batch_frames(self, frames: int) -> None:
+        self._check(self._L.aid_engine_set_max_batch_frames(self._h, int(frames)))
+
+    def params(self) -> dict:
+        out = np.zeros(16, np.int32)
+        self._L.aid_get_params(out.ctypes.data_as(C.POINTER(C.c_int32)))
+        names = ["sample_rate", "nfft", "hop", "nbins", "peak_half_f", "peak_half_t", "peak_min_bin", "dt_min",
+                 "dt_max", "df_min", "df_max", "fanout", "min_votes", "max_rows", "query_max_frames", "seg_tracks"]
+        return dict(zip(names, (int(v) for v in out)))
+
+    @staticmethod
+    def num_frames(n_samples: int) -> int:
+        return 0 if n_samples < 1024 else (n_samples - 1024) // 128 + 1
+
+    @staticmethod
+    def _off(a) -> tuple[np.ndarray, "C._Pointer"]:
+        a = np.ascontiguousarray(a, np.int64)
+        return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+
+    # -- fingerprinting ------------------------------------------------------------------------
+    def hash_capacity(self, sample_off: np.ndarray) -> int:
+        frames = np.maximum((np.diff(sample_off) - 1024) // 128 + 1, 0)
+        return int((((frames + 255) // 256) * 2048 * 8).sum())
+
+    def fingerprint(self, pcm, sample_off, hash_cap: int | None = None):
+        """Ragged host batch -> (hash u32, t_anchor u32, hash_off i64[n+1], status i32[n])."""
+        sample_off, offp = self._off(sample_off)
+        n = len(sample_off) - 1
+        if isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+        cap = self.hash_capacity(sample_off) if hash_cap is None else int(hash_cap)
+        h = np.empty(max(cap, 1), np.uint32)
+        t = np.empty(max(cap, 1), np.uint32)
+        hoff = np.zeros(n + 1, np.int64)
+        st = np.zeros(max(n, 1), np.int32)
+        self._check(self._L.aid_fingerprint_host(self._h, _ptr(pcm), offp, n, h.ctypes.data, t.ctypes.data, cap,
+                                                 hoff.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 st.ctypes.data_as(C.POINTER(C.c_int32))))
+        total = int(hoff[n])
+        return h[:total], t[:total], hoff, st[:n]
+
+    def fingerprint_into(self, pcm, sample_off, h: np.ndarray, t: np.ndarray, hoff: np.ndarray, st: np.ndarray) -> int:
+        """Same, into caller-owned (e.g. pinned) buffers; returns the number of hashes."""
+        sample_off, offp = self._off(sample_off)
+        n = len(sample_off) - 1
+        self._check(self._L.aid_fingerprint_host(self._h, _ptr(pcm), offp, n, _ptr(h), _ptr(t), len(h),
+                                                 C.cast(_ptr(hoff), C.POINTER(C.c_int64)),
+                                                 C.cast(_ptr(st), C.POINTER(C.c_int32))))
+        return int(np.asarray(hoff)[n]) if isinstance(hoff, np.ndarray) else -1
+
+    def fingerprint_dev(self, d_pcm, sample_off, stream=None) -> FpDeviceResult:
+        """PCM already on the device; results stay there (engine-owned, valid until the next call)."""
+        sample_off, offp = self._off(sample_off)
+        res = FpDeviceResult()
+        self._check(self._L.aid_fingerprint_dev(self._h, _ptr(d_pcm), offp, len(sample_off) - 1, C.byref(res),
+                                                _ptr(stream)))
+        return res
+
+    def stft(self, pcm, sample_off) -> np.ndarray:
+        sample_off, offp = self._off(sample_off)
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        frames = int(sum(self.num_frames(int(d)) for d in np.diff(sample_off)))
+        spec = np.zeros((frames, 512), np.float32)
+        self._check(self._L.aid_stft_host(self._h, _ptr(pcm), offp, len(sample_off) - 1, spec.ctypes.data))
+        return spec
+
+    def peaks(self, spec: np.ndarray, frame_off):
+        frame_off, offp = self._off(frame_off)
+        n = len(frame_off) - 1
+        spec = np.ascontiguousarray(spec, np.float32)
+        cap = int((((np.diff(frame_off) + 255) // 256) * 2048).sum())
+        pk = np.zeros(max(cap, 1), np.uint32)
+        poff = np.zeros(n + 1, np.int64)
+        st = np.zeros(max(n, 1), np.int32)
+        self._check(self._L.aid_peaks_host(self._h, spec.ctypes.data, offp, n, pk.ctypes.data, cap,
+                                           poff.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           st.ctypes.data_as(C.POINTER(C.c_int32))))
+        return pk[:int(poff[n])], poff, st[:n]
+
+    def hashes(self, peaks: np.ndarray, peak_off):
+        peak_off, offp = self._off(peak_off)
+        n = len(peak_off) - 1
+        peaks = np.ascontiguousarray(peaks, np.uint32)
+        cap = max(1, len(peaks) * 8)
+        h = np.zeros(cap, np.uint32)
+        t = np.zeros(cap, np.uint32)
+        hoff = np.zeros(n + 1, np.int64)
+        self._check(self._L.aid_hashes_host(self._h, peaks.ctypes.data, offp, n, h.ctypes.data, t.ctypes.data, cap,
+                                            hoff.ctypes.data_as(C.POINTER(C.c_int64))))
+        return h[:int(hoff[n])], t[:int(hoff[n])], hoff
+
+    # -- index --------------------------------------------------------------------------------
+    @staticmethod
+    def _names(names: Sequence[str]):
+        arr = (C.c_char_p * max(len(names), 1))()
+        for i, s in enumerate(names):
+            arr[i] = str(s).encode()
+        return arr
+
+    def index_add(self, pcm, sample_off, names: Sequence[str], device: bool = False) -> np.ndarray:
+        sample_off, offp = self._off(sample_off)
+        n = len(sample_off) - 1
+        if len(names) != n:
+            raise ValueError("one name per track")
+        if not device and isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+        ok = np.zeros(max(n, 1), np.uint8)
+        fn = self._L.aid_index_add_dev if device else self._L.aid_index_add_host
+        self._check(fn(self._h, _ptr(pcm), offp, n, self._names(names), ok.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return ok[:n].astype(bool)
+
+    def index_add_hashes(self, h, t, hash_off, n_frames, names: Sequence[str]) -> np.ndarray:
+        hash_off, offp = self._off(hash_off)
+        n_frames, nfp = self._off(n_frames)
+        n = len(hash_off) - 1
+        h = np.ascontiguousarray(h, np.uint32)
+        t = np.ascontiguousarray(t, np.uint32)
+        ok = np.zeros(max(n, 1), np.uint8)
+        self._check(self._L.aid_index_add_hashes(self._h, h.ctypes.data, t.ctypes.data, offp, nfp, n,
+                                                 self._names(names), ok.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return ok[:n].astype(bool)
+
+    def index_delete(self, name: str) -> bool:
+        rc = self._L.aid_index_delete(self._h, str(name).encode())
+        if rc == -5:
+            return False
+        self._check(rc)
+        return True
+
+    def index_commit(self) -> None:
+        self._check(self._L.aid_index_commit(self._h))
+
+    def index_clear(self) -> None:
+        self._check(self._L.aid_index_clear(self._h))
+
+    def index_stats(self) -> dict:
+        out = np.zeros(8, np.int64)
+        self._check(self._L.aid_index_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return {"tracks": int(out[0]), "postings": int(out[1]), "segments": int(out[2]),
+                "tracks_total": int(out[3]), "device_bytes": int(out[4])}
+
+    def track_name(self, track: int) -> str:
+        buf = C.create_string_buffer(256)
+        rc = self._L.aid_index_track_name(self._h, int(track), buf, 256)
+        if rc < 0:
+            self._check(rc)
+        return buf.value.decode()
+
+    def index_save(self, path: str) -> None:
+        self._check(self._L.aid_index_save(self._h, str(path).encode()))
+
+    def index_load(self, path: str) -> None:
+        self._check(self._L.aid_index_load(self._h, str(path).encode()))
+
+    # -- identification ---------------------------------------------------------------------------
+    def query(self, pcm, sample_off, max_rows: int = MAX_ROWS, device: bool = False):
+        """Ragged batch of vote windows -> (rows[n, max_rows] MATCH_ROW_DTYPE, n_rows i32[n])."""
+        sample_off, offp = self._off(sample_off)
+        n = len(sample_off) - 1
+        if not device and isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+        rows = np.zeros((max(n, 1), max_rows), MATCH_ROW_DTYPE)
+        nr = np.zeros(max(n, 1), np.int32)
+        fn = self._L.aid_query_dev if device else self._L.aid_query_host
+        self._check(fn(self._h, _ptr(pcm), offp, n, rows.ctypes.data, max_rows, nr.ctypes.data_as(C.POINTER(C.c_int32))))
+        return rows[:n], nr[:n]
+
+    def query_hashes(self, h, t, hash_off, max_rows: int = MAX_ROWS):
+        hash_off, offp = self._off(hash_off)
+        n = len(hash_off) - 1
+        h = np.ascontiguousarray(h, np.uint32)
+        t = np.ascontiguousarray(t, np.uint32)
+        rows = np.zeros((max(n, 1), max_rows), MATCH_ROW_DTYPE)
+        nr = np.zeros(max(n, 1), np.int32)
+        self._check(self._L.aid_query_hashes(self._h, h.ctypes.data, t.ctypes.data, offp, n, rows.ctypes.data, max_rows,
+                                             nr.ctypes.data_as(C.POINTER(C.c_int32))))
+        return rows[:n], nr[:n]
+
+    # -- raw device memory (bindings without a CUDA runtime of their own) --------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._L.aid_device_alloc(self._h, int(nbytes), C.byref(p)))
+        return int(p.value or 0)
+
+    def device_free(self, ptr: int) -> None:
+        self._check(self._L.aid_device_free(self._h, int(ptr)))
+
+    def to_device(self, d_ptr: int, arr: np.ndarray) -> None:
+        arr = np.ascontiguousarray(arr)
+        self._check(self._L.aid_copy_to_device(self._h, int(d_ptr), arr.ctypes.data, arr.nbytes))
+
+    def to_host(self, d_ptr: int, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        self._check(self._L.aid_copy_to_host(self._h, out.ctypes.data, int(d_ptr), out.nbytes))
+        return out
+
+    def synth_tracks(self, d_pcm, first_track: int, n_tracks: int, samples_per_track: int, seed: int = 42,
+                     stream=None) -> None:
+        self._check(self._L.aid_synth_tracks_dev(self._h, _ptr(d_pcm), int(first_track), int(n_tracks),
+                                                 int(samples_per_track), int(seed), _ptr(stream)))

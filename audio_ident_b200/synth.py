@@ -23,6 +23,8 @@ QUERY_SEED_OFFSET = 10**6
 def make_track(k: int, seconds: float, *, base_seed: int = BASE_SEED) -> np.ndarray:
     """Track ``k``: float32 array of ``round(seconds * 16000)`` samples."""
     n = int(round(seconds * SAMPLE_RATE))
+    if n <= 0:
+        return np.zeros(0, np.float32)
     rng = np.random.Generator(np.random.PCG64(base_seed + k))
     x = np.zeros(n, dtype=np.float64)
     n_bursts = max(1, int(round(40 * seconds)))

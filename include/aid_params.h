@@ -35,10 +35,15 @@
 #define AID_PEAK_MIN_S    0.001f  /* S must be strictly greater than this             */
 /* a point is a peak iff it passes the two gates above and S equals the maximum of its
  * clipped neighbourhood (all members of an exact tie are peaks).
- * Per-track capacity: AID_PEAK_CAP(frames); exceeding it fails that track. */
-#define AID_PEAK_CAP_PER_FRAME 4
-#define AID_PEAK_CAP_SLACK     64
-#define AID_PEAK_CAP(frames) ((long long)(frames) * AID_PEAK_CAP_PER_FRAME + AID_PEAK_CAP_SLACK)
+ * Capacity rules (they only bind on tie-heavy degenerate input, and fail the track):
+ *   - a frame may hold at most AID_ROW_CAND_CAP points that pass the gates and equal the
+ *     maximum of their own 103-bin row window;
+ *   - every aligned block of AID_PEAK_BLOCK_FRAMES frames [256b, 256b+256) may hold at
+ *     most AID_PEAK_BLOCK_CAP peaks. */
+#define AID_ROW_CAND_CAP       64
+#define AID_PEAK_BLOCK_FRAMES  256
+#define AID_PEAK_BLOCK_CAP     2048
+#define AID_PEAK_CAP(frames) ((((long long)(frames) + AID_PEAK_BLOCK_FRAMES - 1) / AID_PEAK_BLOCK_FRAMES) * AID_PEAK_BLOCK_CAP)
 /* peaks are ordered by (t, f); packed as key = (t << 9) | f */
 #define AID_PEAK_F_BITS   9
 #define AID_MAX_FRAMES    (1 << 22)   /* 4.19 M frames = 9.3 h per track or query */

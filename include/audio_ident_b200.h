@@ -1,0 +1,165 @@
+/* audio_ident_b200.h -- C ABI of the B200 fingerprint-and-match engine (libaudioident_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path. The reference has no FFI for it:
+ * audio-ident-service/app/audio/fingerprint.py reaches the engine by writing a temp file and
+ * executing `olaf_c {store|query|del}` (fingerprint.py:117-125, :185-193, :239-246) with the index
+ * directory in env OLAF_DB (:79-84). Each entry point below names the call it replaces; the Python
+ * binding a maintainer would add is audio_ident_b200/_lib.py (ctypes) and is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns AID_OK (0) or a negative
+ * aid_status and never throws; host output buffers are caller-allocated with an explicit capacity;
+ * `stream` arguments are a cudaStream_t passed as void* (NULL = the engine's own stream).
+ * An engine is bound to one CUDA device; calls on one engine must be serialised by the caller
+ * (the reference serialises writers the same way: routers/ingest.py:52, pipeline.py:294).
+ * There is no CPU fallback: without a usable CUDA device aid_engine_create fails.
+ */
+#ifndef AUDIO_IDENT_B200_H
+#define AUDIO_IDENT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AID_ABI_VERSION 1
+
+typedef enum {
+    AID_OK = 0,
+    AID_E_CUDA = -1,        /* a CUDA call failed; aid_last_error() has the text */
+    AID_E_ARG = -2,         /* bad argument (null pointer, negative size, unsorted offsets ...) */
+    AID_E_CAPACITY = -3,    /* a caller-provided output buffer is too small */
+    AID_E_TOO_LONG = -4,    /* a track or query exceeds the frame limits of aid_params.h */
+    AID_E_NOT_FOUND = -5,   /* unknown track name */
+    AID_E_IO = -6,          /* index directory could not be read or written */
+    AID_E_FORMAT = -7,      /* index files are not ours / wrong version */
+    AID_E_FULL = -8         /* index limits reached */
+} aid_status;
+
+/* per-track status bits written by the fingerprint stages */
+#define AID_TRACK_OK             0
+#define AID_TRACK_PEAK_OVERFLOW  1   /* a capacity rule of aid_params.h was broken (tie-heavy input) */
+#define AID_TRACK_TOO_LONG       2
+#define AID_TRACK_EMPTY          4   /* shorter than one frame: no fingerprints (not an error) */
+
+typedef struct aid_engine aid_engine;
+
+/* One (track, offset) alignment found by a query; what one CSV line of `olaf_c query` carries
+ * (reference fingerprint.py:273-277: count, q_start, q_stop, name, id, ref_start, ref_stop).
+ * Times are frames of AID_FRAME_SECONDS; ref_start = q_first + offset, ref_stop = q_last + offset. */
+typedef struct {
+    int32_t  count;     /* aligned hashes */
+    uint32_t track;     /* engine-wide track number (the reference's "reference_id") */
+    int32_t  offset;    /* t_ref - t_query in frames */
+    int32_t  q_first;   /* first / last query anchor frame among the aligned hashes */
+    int32_t  q_last;
+} aid_match_row;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         aid_abi_version(void);
+const char* aid_strerror(int status);
+/* constants of include/aid_params.h, in the order of oracle/oracle.py PARAM_NAMES; out[16] */
+void        aid_get_params(int32_t* out);
+/* number of CUDA devices visible, or a negative aid_status */
+int         aid_device_count(void);
+
+/* ---- engine -------------------------------------------------------------------------------- */
+int         aid_engine_create(int device, aid_engine** out);
+void        aid_engine_destroy(aid_engine* e);
+const char* aid_last_error(const aid_engine* e);
+/* kernels launched by this engine since creation (bench.py's gpu_launches) */
+int64_t     aid_launch_count(const aid_engine* e);
+/* blocks until the engine's stream is idle */
+int         aid_engine_sync(aid_engine* e);
+/* upper bound on frames processed per internal sub-batch (workspace is about 2.4 KB per frame) */
+int         aid_engine_set_max_batch_frames(aid_engine* e, int64_t frames);
+
+/* ---- fingerprinting: PCM -> (hash, t_anchor) ----------------------------------------------------
+ * Replaces the analysis half of `olaf_c store` / `olaf_c query` (fingerprint.py:117-125, :185-193).
+ * A batch is ragged: track i is pcm[sample_off[i] .. sample_off[i+1]) (16 kHz mono float32).
+ * Outputs are dense: track i owns hash/t_anchor[hash_off[i] .. hash_off[i+1]) in (anchor, target)
+ * order; status[i] carries AID_TRACK_* bits (a failed track has zero hashes). */
+
+/* host buffers in, host buffers out (H2D and D2H inside; pinned memory makes them asynchronous) */
+int aid_fingerprint_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
+                         uint32_t* hash, uint32_t* t_anchor, int64_t hash_cap,
+                         int64_t* hash_off /* [n_tracks+1] */, int32_t* status /* [n_tracks] */);
+
+/* device-resident PCM in; results stay on the device in engine-owned buffers that are valid until
+ * the next call on this engine. Asynchronous on `stream`. Whole batch must fit one sub-batch. */
+typedef struct {
+    const uint32_t* d_hash;       /* [n_hash] */
+    const uint32_t* d_t_anchor;   /* [n_hash] */
+    const uint32_t* d_hash_off;   /* [n_tracks+1] */
+    const uint32_t* d_peaks;      /* [n_peaks] keys (t << 9 | f), (track, t, f) order */
+    const uint32_t* d_peak_off;   /* [n_tracks+1] */
+    const int32_t*  d_status;     /* [n_tracks] */
+    const float*    d_spec;       /* [total_frames][512] */
+    int64_t         total_frames;
+} aid_fp_device_result;
+
+int aid_fingerprint_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off /* host */,
+                        int n_tracks, aid_fp_device_result* out, void* stream);
+
+/* single stages on host buffers (parity tests and tools; same kernels as above) */
+int aid_stft_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
+                  float* spec /* [sum frames][512] */);
+int aid_peaks_host(aid_engine* e, const float* spec, const int64_t* frame_off /* [n+1] */, int n_tracks,
+                   uint32_t* peaks, int64_t peak_cap, int64_t* peak_off /* [n+1] */, int32_t* status);
+int aid_hashes_host(aid_engine* e, const uint32_t* peaks, const int64_t* peak_off /* [n+1] */, int n_tracks,
+                    uint32_t* hash, uint32_t* t_anchor, int64_t hash_cap, int64_t* hash_off /* [n+1] */);
+/* frames a clip of n_samples yields */
+int64_t aid_num_frames(int64_t n_samples);
+
+/* ---- index: `olaf_c store` / `olaf_c del` (fingerprint.py:117-125, :239-246) -------------------- */
+/* Fingerprints the batch and adds each track under names[i] (the reference passes str(uuid),
+ * fingerprint.py:108). ok[i] = 1 if stored. A name that is already present is replaced. */
+int aid_index_add_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
+                       const char* const* names, uint8_t* ok);
+/* Same, PCM already on the device (bulk ingest keeps the PCIe copy out of the way). */
+int aid_index_add_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_tracks,
+                      const char* const* names, uint8_t* ok);
+/* Adds precomputed fingerprints (hash, t_anchor per track, dense with hash_off) -- used to merge
+ * what other ranks fingerprinted and by tests. */
+int aid_index_add_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anchor,
+                         const int64_t* hash_off, const int64_t* n_frames, int n_tracks,
+                         const char* const* names, uint8_t* ok);
+int aid_index_delete(aid_engine* e, const char* name);
+/* makes every added track searchable now (otherwise done lazily by the next query) */
+int aid_index_commit(aid_engine* e);
+int aid_index_clear(aid_engine* e);
+/* out[0] = live tracks, out[1] = postings, out[2] = segments, out[3] = tracks incl. deleted,
+ * out[4] = device bytes held by the index */
+int aid_index_stats(aid_engine* e, int64_t* out);
+/* name of track number `track`; returns its length or a negative aid_status */
+int aid_index_track_name(aid_engine* e, uint32_t track, char* buf, int buf_len);
+/* persistence in the directory the reference calls settings.olaf_lmdb_path (fingerprint.py:79-84) */
+int aid_index_save(aid_engine* e, const char* dir);
+int aid_index_load(aid_engine* e, const char* dir);
+
+/* ---- identification: `olaf_c query` (fingerprint.py:185-193) ---------------------------------------
+ * Each query i is one vote window: pcm[sample_off[i] .. sample_off[i+1]). rows holds max_rows entries
+ * per query (query i at rows + i*max_rows), n_rows[i] of them valid, ordered by
+ * (count desc, track asc, offset asc). max_rows <= AID_MAX_ROWS. */
+int aid_query_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_queries,
+                   aid_match_row* rows, int max_rows, int32_t* n_rows);
+int aid_query_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_queries,
+                  aid_match_row* rows, int max_rows, int32_t* n_rows);
+/* query with precomputed fingerprints (dense, hash_off per query) */
+int aid_query_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anchor, const int64_t* hash_off,
+                     int n_queries, aid_match_row* rows, int max_rows, int32_t* n_rows);
+
+/* ---- helpers for bindings that do not link the CUDA runtime themselves ---------------------- */
+int aid_device_alloc(aid_engine* e, int64_t bytes, void** d_ptr);
+int aid_device_free(aid_engine* e, void* d_ptr);
+int aid_copy_to_device(aid_engine* e, void* d_dst, const void* h_src, int64_t bytes);
+int aid_copy_to_host(aid_engine* e, void* h_dst, const void* d_src, int64_t bytes);
+/* fills d_pcm with the deterministic device-side synthetic corpus used by bench.py: track k of the
+ * batch is global track number first_track + k; all tracks have samples_per_track samples. */
+int aid_synth_tracks_dev(aid_engine* e, float* d_pcm, int64_t first_track, int n_tracks,
+                         int64_t samples_per_track, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIO_IDENT_B200_H */

@@ -134,24 +134,30 @@ static void sliding_max(const float *in, float *out, int64_t n, int64_t stride, 
     }
 }
 
-/* S[T][512] -> keys[] = (t << 9) | f in (t, f) order. Returns the peak count, or -1 if it
- * exceeds cap (the caller passes AID_PEAK_CAP(T)). */
-int64_t aid_oracle_peaks(const float *S, int64_t T, uint32_t *keys, int64_t cap) {
+/* S[T][512] -> keys[] = (t << 9) | f in (t, f) order. Returns the peak count, or -1 if a
+ * capacity rule of aid_params.h is broken (row candidates > AID_ROW_CAND_CAP, or peaks in an
+ * aligned 256-frame block > AID_PEAK_BLOCK_CAP). keys must hold AID_PEAK_CAP(T) entries. */
+int64_t aid_oracle_peaks(const float *S, int64_t T, uint32_t *keys) {
     if (T <= 0) return 0;
     float *m1 = (float *)malloc((size_t)T * NB * sizeof(float));
     float *m2 = (float *)malloc((size_t)T * NB * sizeof(float));
     int64_t *dq = (int64_t *)malloc((size_t)(T > NB ? T : NB) * sizeof(int64_t));
     for (int64_t t = 0; t < T; t++) sliding_max(S + t * NB, m1 + t * NB, NB, 1, AID_PEAK_HALF_F, dq);
     for (int f = 0; f < NB; f++) sliding_max(m1 + f, m2 + f, T, NB, AID_PEAK_HALF_T, dq);
-    int64_t n = 0;
-    for (int64_t t = 0; t < T && n >= 0; t++)
+    int64_t n = 0, in_block = 0;
+    for (int64_t t = 0; t < T && n >= 0; t++) {
+        int row_cand = 0;
+        if (t % AID_PEAK_BLOCK_FRAMES == 0) in_block = 0;
         for (int f = AID_PEAK_MIN_BIN; f < NB; f++) {
             float v = S[t * NB + f];
-            if (v > AID_PEAK_MIN_S && v == m2[t * NB + f]) {
-                if (n >= cap) { n = -1; break; }
+            if (!(v > AID_PEAK_MIN_S) || v != m1[t * NB + f]) continue;
+            if (++row_cand > AID_ROW_CAND_CAP) { n = -1; break; }
+            if (v == m2[t * NB + f]) {
+                if (++in_block > AID_PEAK_BLOCK_CAP) { n = -1; break; }
                 keys[n++] = ((uint32_t)t << AID_PEAK_F_BITS) | (uint32_t)f;
             }
         }
+    }
     free(m1); free(m2); free(dq);
     return n;
 }
@@ -189,7 +195,7 @@ int64_t aid_oracle_fingerprint(const float *pcm, int64_t n_samples, uint32_t *ha
     int64_t cap = AID_PEAK_CAP(T);
     uint32_t *pk = peaks_out ? peaks_out : (uint32_t *)malloc((size_t)cap * sizeof(uint32_t));
     aid_oracle_stft(pcm, n_samples, S);
-    int64_t np = aid_oracle_peaks(S, T, pk, cap);
+    int64_t np = aid_oracle_peaks(S, T, pk);
     int64_t nh = np < 0 ? -1 : aid_oracle_hashes(pk, np, hash, t_anchor);
     if (n_peaks_out) *n_peaks_out = np;
     if (!S_out) free(S);

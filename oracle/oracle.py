@@ -40,7 +40,7 @@ def lib():
         L.aid_oracle_window.argtypes = [f32p]
         L.aid_oracle_num_frames.argtypes = [C.c_int64]; L.aid_oracle_num_frames.restype = C.c_int64
         L.aid_oracle_stft.argtypes = [f32p, C.c_int64, f32p]; L.aid_oracle_stft.restype = C.c_int64
-        L.aid_oracle_peaks.argtypes = [f32p, C.c_int64, u32p, C.c_int64]; L.aid_oracle_peaks.restype = C.c_int64
+        L.aid_oracle_peaks.argtypes = [f32p, C.c_int64, u32p]; L.aid_oracle_peaks.restype = C.c_int64
         L.aid_oracle_hashes.argtypes = [u32p, C.c_int64, u32p, u32p]; L.aid_oracle_hashes.restype = C.c_int64
         L.aid_oracle_fingerprint_batch.argtypes = [f32p, i64p, C.c_int, u32p, u32p, i64p, i64p, i64p, C.c_int]
         L.aid_oracle_fingerprint_batch.restype = C.c_int
@@ -78,7 +78,7 @@ def num_frames(n: int) -> int:
 
 
 def peak_cap(frames: int) -> int:
-    return frames * 4 + 64
+    return ((frames + 255) // 256) * 2048
 
 
 def stft(pcm: np.ndarray) -> np.ndarray:
@@ -95,8 +95,8 @@ def peaks(S: np.ndarray) -> np.ndarray:
     S = np.ascontiguousarray(S, np.float32)
     T = S.shape[0]
     cap = peak_cap(T)
-    keys = np.zeros(cap, np.uint32)
-    n = lib().aid_oracle_peaks(_p(S, C.c_float), T, _p(keys, C.c_uint32), cap)
+    keys = np.zeros(max(1, cap), np.uint32)
+    n = lib().aid_oracle_peaks(_p(S, C.c_float), T, _p(keys, C.c_uint32))
     if n < 0:
         raise OverflowError("peak capacity exceeded")
     return keys[:n].copy()
@@ -120,7 +120,7 @@ def fingerprint_batch(pcm: np.ndarray, sample_off: np.ndarray, threads: int = 0)
     sample_off = np.ascontiguousarray(sample_off, np.int64)
     n = len(sample_off) - 1
     frames = np.array([num_frames(int(sample_off[i + 1] - sample_off[i])) for i in range(n)], np.int64)
-    caps = (frames * 4 + 64) * 8
+    caps = ((frames + 255) // 256) * 2048 * 8
     slot = np.zeros(n + 1, np.int64); slot[1:] = np.cumsum(caps)
     h = np.zeros(max(1, int(slot[-1])), np.uint32); t = np.zeros_like(h)
     nh = np.zeros(n, np.int64); npk = np.zeros(n, np.int64)
