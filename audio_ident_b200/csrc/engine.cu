@@ -105,6 +105,8 @@ extern "C" void aid_engine_destroy(aid_engine* e) {
     cudaDeviceSynchronize();
     if (e->index) aid_index_free(e, e->index);
     for (int i = 0; i < 2; i++) e->slot[i].release();
+    for (auto& r : e->stage_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
     e->d_window.release(); e->d_twiddle.release();
     delete e;
 }
@@ -202,6 +204,48 @@ int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, in
     return AID_OK;
 }
 
+namespace {
+struct StageTimer {          // records an event pair around a group of launches when timing is on
+    aid_engine* e; cudaStream_t st; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t take(aid_engine* e) {
+        cudaEvent_t ev = nullptr;
+        if (!e->event_pool.empty()) { ev = e->event_pool.back(); e->event_pool.pop_back(); }
+        else if (cudaEventCreate(&ev) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+        return ev;
+    }
+    StageTimer(aid_engine* e_, cudaStream_t st_, int stage_) : e(e_), st(st_), stage(stage_) {
+        if (!e->timing) return;
+        a = take(e); b = take(e);
+        if (a) cudaEventRecord(a, st);
+    }
+    ~StageTimer() {
+        if (!e->timing || !a || !b) return;
+        cudaEventRecord(b, st);
+        e->stage_recs.push_back({stage, a, b});
+    }
+};
+}
+
+extern "C" int aid_engine_set_stage_timing(aid_engine* e, int on) {
+    if (!e) return AID_E_ARG;
+    e->timing = on != 0;
+    return AID_OK;
+}
+
+extern "C" int aid_engine_stage_times(aid_engine* e, double* ms, int64_t* launches) {
+    if (!e || !ms || !launches) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    for (auto& r : e->stage_recs) {
+        float t = 0.0f;
+        AID_CUDA(e, cudaEventSynchronize(r.b));
+        AID_CUDA(e, cudaEventElapsedTime(&t, r.a, r.b));
+        if (r.stage >= 0 && r.stage < 4) { ms[r.stage] += t; launches[r.stage] += 1; }
+        e->event_pool.push_back(r.a); e->event_pool.push_back(r.b);
+    }
+    e->stage_recs.clear();
+    return AID_OK;
+}
+
 // misc words: [0] n_peaks_total, [1] hash overflow flag, [2] n_hash_total
 int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d_pcm, cudaStream_t st) {
     const int n = plan.n_tracks;
@@ -211,26 +255,33 @@ int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d
     const size_t b0 = (size_t)((char*)s.d_punits - (char*)s.d_sunits);
     const size_t b1 = (size_t)((char*)s.d_first_punit - (char*)s.d_punits);
     const size_t b2 = (size_t)(n + 1) * sizeof(uint32_t);
+    AID_CUDA(e, cudaEventSynchronize(s.done));      // the previous upload from this staging buffer has landed
     if (nsu) memcpy(h, plan.sunits.data(), (size_t)nsu * sizeof(aid_stft_unit));
     if (npu) memcpy(h + b0, plan.punits.data(), (size_t)npu * sizeof(aid_peak_unit));
     memcpy(h + b0 + b1, plan.first_punit.data(), b2);
     AID_CUDA(e, cudaMemcpyAsync(s.desc.p, h, b0 + b1 + b2, cudaMemcpyHostToDevice, st));
+    AID_CUDA(e, cudaEventRecord(s.done, st));
     AID_CUDA(e, cudaMemsetAsync(s.status.p, 0, (size_t)(n + 1) * sizeof(int32_t), st));
     AID_CUDA(e, cudaMemsetAsync(s.misc.p, 0, 256, st));
 
     uint32_t* unit_cnt = s.unit_pos.as<uint32_t>();
     uint32_t* unit_pos = unit_cnt + (npu + 1);
     uint32_t* misc = s.misc.as<uint32_t>();
-    AID_CUDA(e, aid_launch_stft(e->tables, d_pcm, s.d_sunits, nsu, s.spec.as<float>(), st));
-    AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, npu, s.slots.as<uint32_t>(), unit_cnt,
-                                 s.status.as<int32_t>(), st));
+    { StageTimer tm(e, st, 0);
+      AID_CUDA(e, aid_launch_stft(e->tables, d_pcm, s.d_sunits, nsu, s.spec.as<float>(), st)); }
+    { StageTimer tm(e, st, 1);
+      AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, npu, s.slots.as<uint32_t>(), unit_cnt,
+                                   s.status.as<int32_t>(), st)); }
     // unit counts -> dense positions (unit_pos[npu] = total peaks)
+    { StageTimer tm2(e, st, 2);
     AID_CUDA(e, cudaMemsetAsync(unit_cnt + npu, 0, sizeof(uint32_t), st));
     AID_CUDA(e, aid_launch_scan_u32(unit_cnt, unit_pos, npu + 1, s.scan_tmp.as<uint32_t>(), misc + 0, nullptr, st));
     AID_CUDA(e, aid_launch_peak_compact(s.slots.as<uint32_t>(), unit_cnt, unit_pos, s.d_punits, npu,
                                         s.peaks.as<uint32_t>(), s.peak_track.as<uint32_t>(), st));
     AID_CUDA(e, aid_launch_gather_u32(unit_pos, s.d_first_punit, s.peak_off.as<uint32_t>(), n + 1, st));
+    }
     // per-anchor hash counts -> dense positions (pos[n_peaks] = total hashes)
+    StageTimer tm3(e, st, 3);
     AID_CUDA(e, aid_launch_hash_count(s.peaks.as<uint32_t>(), s.peak_track.as<uint32_t>(), s.peak_off.as<uint32_t>(),
                                       misc + 0, plan.peak_cap, s.pos.as<uint32_t>(), st));
     AID_CUDA(e, aid_launch_scan_u32(s.pos.as<uint32_t>(), s.pos.as<uint32_t>(), plan.peak_cap + 1,

@@ -77,6 +77,11 @@ struct aid_engine {
     DevBuf d_window, d_twiddle;
     aid_tables tables{};
     Index* index = nullptr;
+    // optional per-stage timing (aid_engine_set_stage_timing)
+    bool timing = false;
+    struct StageRec { int stage; cudaEvent_t a, b; };
+    std::vector<StageRec> stage_recs;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 // engine.cu internals used by index.cu / match.cu

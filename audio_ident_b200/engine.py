@@ -94,6 +94,16 @@ class Engine:
     def set_max_batch_frames(self, frames: int) -> None:
         self._check(self._L.aid_engine_set_max_batch_frames(self._h, int(frames)))
 
+    def set_stage_timing(self, on: bool) -> None:
+        self._check(self._L.aid_engine_set_stage_timing(self._h, int(bool(on))))
+
+    def stage_times(self) -> dict:
+        """{stage: (milliseconds, timed launches)} accumulated since the last call; waits for the work."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        self._check(self._L.aid_engine_stage_times(self._h, ms, n))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(("stft", "peaks", "compact", "hash"))}
+
     def params(self) -> dict:
         out = np.zeros(16, np.int32)
         self._L.aid_get_params(out.ctypes.data_as(C.POINTER(C.c_int32)))

@@ -73,6 +73,12 @@ int64_t     aid_launch_count(const aid_engine* e);
 int         aid_engine_sync(aid_engine* e);
 /* upper bound on frames processed per internal sub-batch (workspace is about 2.4 KB per frame) */
 int         aid_engine_set_max_batch_frames(aid_engine* e, int64_t frames);
+/* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline numbers).
+ * Stages: 0 = STFT kernel, 1 = peak kernel, 2 = peak compaction (scan + copy), 3 = hasher (count + scan +
+ * write). aid_engine_stage_times waits for the recorded work, adds the elapsed milliseconds and the number
+ * of timed launches per stage into ms[4] / launches[4], and forgets the records. */
+int         aid_engine_set_stage_timing(aid_engine* e, int on);
+int         aid_engine_stage_times(aid_engine* e, double* ms, int64_t* launches);
 
 /* ---- fingerprinting: PCM -> (hash, t_anchor) ----------------------------------------------------
  * Replaces the analysis half of `olaf_c store` / `olaf_c query` (fingerprint.py:117-125, :185-193).
