@@ -40,31 +40,44 @@ __host__ __device__ constexpr int bitrev5(int i) {
     return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
 }
 
-// In-register 32-point complex FFT, radix-2 decimation in frequency, fully unrolled so every
-// twiddle is an immediate. Output X[k] is left in element bitrev5(k).
-__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int half = 16 >> s;
-#pragma unroll
-        for (int g = 0; g < (1 << s); g++) {
-#pragma unroll
-            for (int k = 0; k < half; k++) {
-                const int a = g * 2 * half + k, b = a + half;
-                const int tw = k << s;                       // W_32^tw
-                const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
-                re[a] = ar + br; im[a] = ai + bi;
-                const float dr = ar - br, di = ai - bi;
-                if (tw == 0) { re[b] = dr; im[b] = di; }
-                else if (tw == 8) { re[b] = di; im[b] = -dr; }            // * (-i)
-                else {
-                    const float c = kC32[tw], sn = kS32[tw];              // (dr + i di)(c - i sn)
-                    re[b] = fmaf(dr, c, di * sn);
-                    im[b] = fmaf(di, c, -dr * sn);
-                }
-            }
-        }
+// In-register 32-point complex FFT, radix-2 decimation in time, fully unrolled so every twiddle is an
+// immediate. Input x[n] sits in element bitrev5(n); output X[k] is left in element k. A general butterfly
+// costs 6 FMA: X = a + w*b (4 FMA), Y = 2a - X (2 FMA).
+template <int A, int B, int TW>
+__device__ __forceinline__ void butterfly(float (&re)[32], float (&im)[32]) {
+    const float ar = re[A], ai = im[A], br = re[B], bi = im[B];
+    if constexpr (TW == 0) {
+        re[A] = ar + br; im[A] = ai + bi; re[B] = ar - br; im[B] = ai - bi;
+    } else if constexpr (TW == 8) {                          // w = -i
+        re[A] = ar + bi; im[A] = ai - br; re[B] = ar - bi; im[B] = ai + br;
+    } else {
+        constexpr float c = kC32[TW], sn = kS32[TW];         // w = c - i sn
+        const float xr = fmaf(bi, sn, fmaf(br, c, ar));
+        const float xi = fmaf(bi, c, fmaf(-br, sn, ai));
+        re[A] = xr; im[A] = xi;
+        re[B] = fmaf(2.0f, ar, -xr); im[B] = fmaf(2.0f, ai, -xi);
     }
+}
+
+template <int S, int I>
+__device__ __forceinline__ void stage(float (&re)[32], float (&im)[32]) {
+    if constexpr (I < 16) {
+        constexpr int half = 1 << S;
+        constexpr int g = I / half, k = I % half;
+        butterfly<g * 2 * half + k, g * 2 * half + k + half, k * (16 >> S)>(re, im);
+        stage<S, I + 1>(re, im);
+    }
+}
+
+__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+    stage<0, 0>(re, im); stage<1, 0>(re, im); stage<2, 0>(re, im); stage<3, 0>(re, im); stage<4, 0>(re, im);
+}
+
+// log(1 + s4/4) for s4 >= 0: one FFMA, one MUFU.LG2 (the argument is >= 1, so no denormal handling), one FMUL
+__device__ __forceinline__ float log1p_quarter(float s4) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(0.25f, s4, 1.0f)));
+    return y * 0.69314718055994531f;
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -72,7 +85,7 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
        const float* __restrict__ pcm, const aid_stft_unit* __restrict__ units, int n_units,
        float* __restrict__ spec) {
     __shared__ float2 s_tw[32 * 32];
-    __shared__ float s_tile[kWarpsPerCta][2][kTileFloats];
+    __shared__ float2 s_tile[kWarpsPerCta][kTileFloats];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_tw[i] = twiddle[i];
@@ -86,76 +99,64 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
 #pragma unroll
     for (int j = 0; j < 32; j++) w[j] = __ldg(window + lane + 32 * j);
 
-    // lane's samples: x[first + 32*m + lane], first = frame0 * 128
-    const float* x = pcm + u.pcm_begin;
+    // lane's samples: xp[32*m], m = 0.. ; rem = samples left from xp (32-bit: a track has < 2^31 samples)
     const int64_t first = (int64_t)u.frame0 * AID_HOP + lane;
-    const int64_t n = u.n_samples;
-    auto sample = [&](int m) -> float {
-        const int64_t idx = first + 32 * (int64_t)m;
-        return idx < n ? __ldg(x + idx) : 0.0f;
-    };
+    const float* xp = pcm + u.pcm_begin + first;
+    int rem = (int)(u.n_samples - first);
 
     float ring[36];
 #pragma unroll
-    for (int j = 0; j < 36; j++) ring[j] = sample(j);
+    for (int j = 0; j < 36; j++) ring[j] = 32 * j < rem ? __ldg(xp + 32 * j) : 0.0f;
 
-    float* tile_re = s_tile[warp][0];
-    float* tile_im = s_tile[warp][1];
+    float2* tile = s_tile[warp];
     const int partner = (32 - lane) & 31;
+    float* row_a = spec + u.spec_row * AID_NBINS + lane;
 
     for (int p = 0; p < u.n_frames; p += 2) {
         float nxt[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) nxt[j] = sample(4 * p + 36 + j);
+        for (int j = 0; j < 8; j++) nxt[j] = 32 * (36 + j) < rem ? __ldg(xp + 32 * (36 + j)) : 0.0f;
+        xp += 2 * AID_HOP;
+        rem -= 2 * AID_HOP;
 
         float re[32], im[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) { re[j] = w[j] * ring[j]; im[j] = w[j] * ring[j + 4]; }
+        for (int j = 0; j < 32; j++) { re[bitrev5(j)] = w[j] * ring[j]; im[bitrev5(j)] = w[j] * ring[j + 4]; }
 
-        fft32(re, im);                                   // over n2; Y[k1] in element bitrev5(k1)
+        fft32(re, im);                                   // over n2: Y[k1] in element k1
 
         // twiddle W_1024^(lane * k1), then scatter Y[k1] to tile[k1][lane]
+        tile[lane] = make_float2(re[0], im[0]);
 #pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) {
-            const int e = bitrev5(k1);
-            float yr = re[e], yi = im[e];
-            if (k1 != 0) {
-                const float2 t = s_tw[k1 * 32 + lane];
-                const float r2 = yr * t.x - yi * t.y;
-                yi = fmaf(yr, t.y, yi * t.x);
-                yr = r2;
-            }
-            tile_re[k1 * kTileStride + lane] = yr;
-            tile_im[k1 * kTileStride + lane] = yi;
+        for (int k1 = 1; k1 < 32; k1++) {
+            const float2 t = s_tw[k1 * 32 + lane];
+            tile[k1 * kTileStride + lane] = make_float2(fmaf(re[k1], t.x, -im[k1] * t.y), fmaf(re[k1], t.y, im[k1] * t.x));
         }
         __syncwarp();
 #pragma unroll
         for (int n1 = 0; n1 < 32; n1++) {                // lane = k1 gathers all n1
-            re[n1] = tile_re[lane * kTileStride + n1];
-            im[n1] = tile_im[lane * kTileStride + n1];
+            const float2 z = tile[lane * kTileStride + n1];
+            re[bitrev5(n1)] = z.x; im[bitrev5(n1)] = z.y;
         }
         __syncwarp();
 
-        fft32(re, im);                                   // over n1; Z[lane + 32*k2] in element bitrev5(k2)
+        fft32(re, im);                                   // over n1: Z[lane + 32*k2] in element k2
 
-        float* row_a = spec + (u.spec_row + p) * AID_NBINS;
         const bool has_b = p + 1 < u.n_frames;
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
-            const int e = bitrev5(k2);
-            const float zr = re[e], zi = im[e];
+            const float zr = re[k2], zi = im[k2];
             // mirror Z[1024 - k]: lane (32-k1)&31, k2' = 31 - k2 (k1 != 0) or (32 - k2)&31 (k1 == 0)
-            float mr = __shfl_sync(AID_FULL_MASK, re[bitrev5(31 - k2)], partner);
-            float mi = __shfl_sync(AID_FULL_MASK, im[bitrev5(31 - k2)], partner);
-            if (lane == 0) { mr = re[bitrev5((32 - k2) & 31)]; mi = im[bitrev5((32 - k2) & 31)]; }
+            const float sr = __shfl_sync(AID_FULL_MASK, re[31 - k2], partner);
+            const float si = __shfl_sync(AID_FULL_MASK, im[31 - k2], partner);
+            const float mr = lane == 0 ? re[(32 - k2) & 31] : sr;
+            const float mi = lane == 0 ? im[(32 - k2) & 31] : si;
             const float ar = zr + mr, ai = zi - mi;      // 2 * X_a[k]
             const float br = zr - mr, bi = zi + mi;      // 2i * X_b[k]
-            const float pa = 0.25f * fmaf(ar, ar, ai * ai);
-            const float pb = 0.25f * fmaf(br, br, bi * bi);
-            const int k = lane + 32 * k2;
-            row_a[k] = __logf(1.0f + pa);
-            if (has_b) row_a[AID_NBINS + k] = __logf(1.0f + pb);
+            row_a[32 * k2] = log1p_quarter(fmaf(ar, ar, ai * ai));
+            if (has_b) row_a[AID_NBINS + 32 * k2] = log1p_quarter(fmaf(br, br, bi * bi));
         }
+        row_a += 2 * AID_NBINS;
 
 #pragma unroll
         for (int j = 0; j < 28; j++) ring[j] = ring[j + 8];
