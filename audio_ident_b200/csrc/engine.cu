@@ -204,28 +204,6 @@ int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, in
     return AID_OK;
 }
 
-namespace {
-struct StageTimer {          // records an event pair around a group of launches when timing is on
-    aid_engine* e; cudaStream_t st; int stage; cudaEvent_t a = nullptr, b = nullptr;
-    static cudaEvent_t take(aid_engine* e) {
-        cudaEvent_t ev = nullptr;
-        if (!e->event_pool.empty()) { ev = e->event_pool.back(); e->event_pool.pop_back(); }
-        else if (cudaEventCreate(&ev) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
-        return ev;
-    }
-    StageTimer(aid_engine* e_, cudaStream_t st_, int stage_) : e(e_), st(st_), stage(stage_) {
-        if (!e->timing) return;
-        a = take(e); b = take(e);
-        if (a) cudaEventRecord(a, st);
-    }
-    ~StageTimer() {
-        if (!e->timing || !a || !b) return;
-        cudaEventRecord(b, st);
-        e->stage_recs.push_back({stage, a, b});
-    }
-};
-}
-
 extern "C" int aid_engine_set_stage_timing(aid_engine* e, int on) {
     if (!e) return AID_E_ARG;
     e->timing = on != 0;
@@ -239,7 +217,7 @@ extern "C" int aid_engine_stage_times(aid_engine* e, double* ms, int64_t* launch
         float t = 0.0f;
         AID_CUDA(e, cudaEventSynchronize(r.b));
         AID_CUDA(e, cudaEventElapsedTime(&t, r.a, r.b));
-        if (r.stage >= 0 && r.stage < 4) { ms[r.stage] += t; launches[r.stage] += 1; }
+        if (r.stage >= 0 && r.stage < 8) { ms[r.stage] += t; launches[r.stage] += 1; }
         e->event_pool.push_back(r.a); e->event_pool.push_back(r.b);
     }
     e->stage_recs.clear();

@@ -84,6 +84,28 @@ struct aid_engine {
     std::vector<cudaEvent_t> event_pool;
 };
 
+// records a CUDA-event pair around a group of launches when stage timing is on
+struct StageTimer {          // records an event pair around a group of launches when timing is on
+    aid_engine* e; cudaStream_t st; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t take(aid_engine* e) {
+        cudaEvent_t ev = nullptr;
+        if (!e->event_pool.empty()) { ev = e->event_pool.back(); e->event_pool.pop_back(); }
+        else if (cudaEventCreate(&ev) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+        return ev;
+    }
+    StageTimer(aid_engine* e_, cudaStream_t st_, int stage_) : e(e_), st(st_), stage(stage_) {
+        if (!e->timing) return;
+        a = take(e); b = take(e);
+        if (a) cudaEventRecord(a, st);
+    }
+    ~StageTimer() {
+        if (!e->timing || !a || !b) return;
+        cudaEventRecord(b, st);
+        e->stage_recs.push_back({stage, a, b});
+    }
+};
+
+
 // engine.cu internals used by index.cu / match.cu
 int aid_fail_cuda(aid_engine* e, cudaError_t ce, const char* what);
 #define AID_CUDA(e, call) do { cudaError_t ce_ = (call); if (ce_ != cudaSuccess) return aid_fail_cuda((e), ce_, #call); } while (0)

@@ -199,6 +199,7 @@ static int build_segment(aid_engine* e, Index* ix, Segment* s, cudaStream_t st) 
     uint32_t* bucket = s->bucket.as<uint32_t>();
     AID_CUDA(e, cudaMemsetAsync(bucket, 0, (size_t)(kBuckets + 1) * 4, st));
     if (n > 0) {
+        StageTimer tm(e, st, 6);
         const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
         k_hist<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), n, bucket);
         AID_CUDA(e, aid_launch_scan_u32(bucket, bucket, kBuckets + 1, ix->scan_tmp.as<uint32_t>(), nullptr, nullptr, st));

@@ -299,10 +299,12 @@ static int match_device(aid_engine* e, const uint32_t* d_hash, const uint32_t* d
     AID_CUDA(e, ix->cand_n.ensure((size_t)n_cta * 4));
     AID_CUDA(e, ix->rows.ensure((size_t)n_q * max_rows * sizeof(aid_match_row)));
     AID_CUDA(e, ix->rows_n.ensure((size_t)n_q * 4));
+    { StageTimer tm(e, st, 4);
     k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
-                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>());
+                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>()); }
+    { StageTimer tm(e, st, 5);
     k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
-                                     max_rows, ix->rows.as<aid_match_row>(), ix->rows_n.as<int32_t>());
+                                     max_rows, ix->rows.as<aid_match_row>(), ix->rows_n.as<int32_t>()); }
     AID_CUDA(e, cudaGetLastError());
     e->launches += 2;
     AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.p, (size_t)n_q * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, st));

@@ -99,10 +99,11 @@ class Engine:
 
     def stage_times(self) -> dict:
         """{stage: (milliseconds, timed launches)} accumulated since the last call; waits for the work."""
-        ms = (C.c_double * 4)()
-        n = (C.c_int64 * 4)()
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
         self._check(self._L.aid_engine_stage_times(self._h, ms, n))
-        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(("stft", "peaks", "compact", "hash"))}
+        names = ("stft", "peaks", "compact", "hash", "match", "rank", "index_build")
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(names)}
 
     def params(self) -> dict:
         out = np.zeros(16, np.int32)

@@ -40,20 +40,35 @@ def rows_to_array(rows: np.ndarray, n: np.ndarray, to_global: np.ndarray) -> np.
     return out
 
 
-def merge_rows(blocks: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
-    """blocks int64 [P, n_q, 50, 5] -> (merged [n_q, 50, 5], n_rows [n_q]); same arithmetic on every rank."""
+_OFF_BIAS = 1 << 18          # offsets are > -2^18
+
+
+def _sort_keys(r):
+    """(count desc, track asc, offset asc) as one ascending int64 key; rows with count < 0 sort last.
+    Works on numpy arrays and torch tensors alike (r[..., 5] integer)."""
+    count, track, offset = r[..., 0], r[..., 1], r[..., 2]
+    key = ((0xFFFFF - count.clip(0, 0xFFFFF)) << 44) | (track.clip(0, (1 << 25) - 1) << 19) | (offset + _OFF_BIAS).clip(0, (1 << 19) - 1)
+    return key + (count < 0) * (1 << 62)
+
+
+def merge_rows(blocks):
+    """blocks int64 [P, n_q, 50, 5] (numpy or torch) -> (merged [n_q, 50, 5], n_rows [n_q]); the same arithmetic on
+    every rank, vectorised over the whole query batch."""
+    if isinstance(blocks, np.ndarray):
+        P, n_q = blocks.shape[0], blocks.shape[1]
+        allr = np.transpose(blocks, (1, 0, 2, 3)).reshape(n_q, P * MAX_ROWS, 5)
+        order = np.argsort(_sort_keys(allr), axis=1, kind="stable")[:, :MAX_ROWS]
+        merged = np.take_along_axis(allr, order[:, :, None], axis=1)
+        n_rows = (merged[:, :, 0] >= 0).sum(axis=1).astype(np.int32)
+        merged[merged[:, :, 0] < 0] = -1
+        return merged, n_rows
+    import torch
     P, n_q = blocks.shape[0], blocks.shape[1]
-    allr = np.transpose(blocks, (1, 0, 2, 3)).reshape(n_q, P * MAX_ROWS, 5)
-    merged = np.full((n_q, MAX_ROWS, 5), -1, np.int64)
-    n_rows = np.zeros(n_q, np.int32)
-    for q in range(n_q):
-        r = allr[q]
-        r = r[r[:, 0] >= 0]
-        if len(r) == 0:
-            continue
-        order = np.lexsort((r[:, 2], r[:, 1], -r[:, 0]))[:MAX_ROWS]
-        merged[q, :len(order)] = r[order]
-        n_rows[q] = len(order)
+    allr = blocks.permute(1, 0, 2, 3).reshape(n_q, P * MAX_ROWS, 5)
+    order = torch.sort(_sort_keys(allr), dim=1, stable=True).indices[:, :MAX_ROWS]
+    merged = torch.gather(allr, 1, order[:, :, None].expand(-1, -1, 5))
+    n_rows = (merged[:, :, 0] >= 0).sum(dim=1).to(torch.int32)
+    merged = torch.where(merged[:, :, :1] < 0, torch.full_like(merged, -1), merged)
     return merged, n_rows
 
 
@@ -82,17 +97,21 @@ class ShardedIdentifier:
         return ok
 
     # ---- identify: local probe + one all-gather + identical merge everywhere
-    def _exchange(self, local: np.ndarray) -> np.ndarray:
-        if self.world == 1:
+    def _exchange(self, local: np.ndarray):
+        """local rows -> [P, n_q, 50, 5]; on a CUDA device the block stays a torch tensor so the merge runs there."""
+        if self.world == 1 and self.device is None:
             return local[None]
         import torch
         import torch.distributed as dist
         t = torch.from_numpy(np.ascontiguousarray(local))
         if self.device is not None:
-            t = t.to(self.device)
+            t = t.to(self.device, non_blocking=True)
+        if self.world == 1:
+            return t[None]
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t, group=self.group)
-        return out.cpu().numpy().reshape((self.world,) + tuple(t.shape))
+        out = out.reshape((self.world,) + tuple(t.shape))
+        return out if self.device is not None else out.numpy()
 
     def query(self, pcm, sample_off, device: bool = False):
         rows, n = self.backend.query(pcm, sample_off, device=device)

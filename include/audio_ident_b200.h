@@ -75,8 +75,9 @@ int         aid_engine_sync(aid_engine* e);
 int         aid_engine_set_max_batch_frames(aid_engine* e, int64_t frames);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline numbers).
  * Stages: 0 = STFT kernel, 1 = peak kernel, 2 = peak compaction (scan + copy), 3 = hasher (count + scan +
- * write). aid_engine_stage_times waits for the recorded work, adds the elapsed milliseconds and the number
- * of timed launches per stage into ms[4] / launches[4], and forgets the records. */
+ * write), 4 = matcher (k_match), 5 = ranking (k_rank), 6 = index build, 7 = unused.
+ * aid_engine_stage_times waits for the recorded work, adds the elapsed milliseconds and the number
+ * of timed launches per stage into ms[8] / launches[8], and forgets the records. */
 int         aid_engine_set_stage_timing(aid_engine* e, int on);
 int         aid_engine_stage_times(aid_engine* e, double* ms, int64_t* launches);
 
