@@ -4,84 +4,91 @@
 // reference audio-ident-service/app/audio/fingerprint.py:117-125). Definition of the result:
 // oracle/aid_oracle.c aid_oracle_peaks(); bit-exact on the same spectrogram.
 //
-// Design (DESIGN.md "Peak kernel"): one CTA streams the rows of one aligned 256-frame block of one
-// track (plus a 12-row halo on each side).
-//  * Row pass: a warp owns a whole 512-bin row, 16 contiguous bins per lane. The 103-bin sliding
-//    maximum M1 is built from per-lane prefix/suffix maxima and 38 warp shuffles (no shared memory),
-//    written into a 40-row shared-memory ring, and the row's candidates (S == M1, gates passed) are
-//    queued with one shared-memory atomic per row.
-//  * Column pass: a candidate is a peak iff no M1 value in the 24 neighbouring rows of its column
-//    exceeds it; only candidates (about 1 % of the points) pay for the time direction.
-//  * Candidates and peaks travel through small shared-memory queues; the block's peaks (a few dozen) are
-//    put in (t, f) order by a bitonic network sized to their count before they are written.
-// HBM traffic: every spectrogram row is read once per block (+24/256 halo rows); peaks out are noise.
+// Design (DESIGN.md "Peak kernel"): one CTA (8 warps) streams the rows of one aligned 256-frame block of one
+// track plus a 12-row halo on each side, 16 rows per step (two per warp, both loads in flight together), and
+// keeps only two tiny per-row summaries in shared memory -- never the spectrogram itself:
+//    A [row][g]  = maximum of the aligned 16-bin group g (32 groups per row, one per lane)
+//    C5[row][g]  = max(A[g-2 .. g+2])
+//  * Row pass (a warp owns a whole 2 KB row, 16 contiguous bins per lane): one max-reduction per lane gives A,
+//    four shuffles give C5. A point can only be the maximum of its 103-bin window if it equals its group
+//    maximum and that equals C5 (the five groups lie inside every window of the group). Such "group
+//    candidates" (~1.6 % of the points) are queued with one shared-memory atomic per row.
+//  * Column pass 1 (one thread per candidate): the whole groups inside the window -- g-2..g+2, plus g-3 or g+3
+//    when the bin sits at the edge of its group -- are tested on all 25 rows using C5 and A: 24-50
+//    shared-memory loads, rejects ~96 %.
+//  * Column pass 2 (one warp per survivor, one lane per row): the at most 30 window bins outside the whole
+//    groups are re-read from global memory (streamed moments ago: L2 hits) and tested exactly.
+//  * Peaks are appended in no particular order and put in (t, f) order by a bitonic network sized to their count.
+// Every comparison is <= against the candidate's own value, so exact ties behave as the specification says.
+// HBM traffic: every spectrogram row is read once per block (+24/256 halo rows, L2 hits); peaks out are noise.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;       // rows per step
-constexpr int kRing = 40;                   // M1 rows kept in shared memory (>= kWarps + 24)
-constexpr int kQueue = 2048;                // candidates waiting for the column pass (<= 28 rows x 64)
-
-// ring rows are stored permuted so that the 16-bins-per-lane register layout writes conflict-free
-// 16-byte chunks: bin f = 16*l + 4*q + c  ->  128*q + 4*l + c
-__device__ __forceinline__ int phys(int f) { return ((f >> 2) & 3) * 128 + (f >> 4) * 4 + (f & 3); }
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kStep = 2 * kWarps;           // rows per step
+constexpr int kRing = 56;                   // rows of A / C5 kept (>= 2 * kStep + 24)
+constexpr int kRingStride = kRing + 1;      // [group][row slot], odd stride: conflict-free both ways
+constexpr int kQ1 = (kStep + 12) * AID_ROW_CAND_CAP;   // group candidates waiting for column pass 1
+constexpr int kQ2 = 256;                    // survivors waiting for column pass 2 (overflow is handled inline)
+constexpr int kHalfF = AID_PEAK_HALF_F, kHalfT = AID_PEAK_HALF_T;
 
 struct Smem {
-    float ring[kRing][AID_NBINS];
-    uint32_t queue[2][kQueue];
+    float A[32 * kRingStride];
+    float C5[32 * kRingStride];
+    uint32_t q1[2][kQ1];
+    uint32_t q2[kQ2];
     uint32_t peaks[AID_PEAK_BLOCK_CAP];
-    int qn[2];
+    int n1[2];
+    int n2;
     int npeaks;
     int fail;
 };
 
-// One warp: row of S -> M1 row into the ring, row candidates (S == M1, gates passed) into the queue.
-// Out-of-range shuffles return the lane's own value, which is never above the lane's own group maximum and
-// therefore never changes a window maximum: the clipped window needs no masking.
-__device__ __forceinline__ void row_pass(Smem& sm, const float* __restrict__ srow, int row, bool store, bool emit,
-                                         int qsel, int lane) {
-    float v[16];
-    const float4* src = reinterpret_cast<const float4*>(srow) + lane * 4;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float4 x = __ldg(src + q);
-        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-    }
-    float pre[16], suf[16];
-    pre[0] = v[0];
-#pragma unroll
-    for (int i = 1; i < 16; i++) pre[i] = fmaxf(pre[i - 1], v[i]);
-    suf[15] = v[15];
-#pragma unroll
-    for (int i = 14; i >= 0; i--) suf[i] = fmaxf(suf[i + 1], v[i]);
-    const float A = pre[15];
-    const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
-    const float am3 = __shfl_up_sync(AID_FULL_MASK, A, 3);
-    const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
-    const float ap3 = __shfl_down_sync(AID_FULL_MASK, A, 3);
-    const float c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
-    const float c5l = fmaxf(c5, am3), c5r = fmaxf(c5, ap3);
+// Are all bins of `row` in [lo, hi] (clipped to the spectrogram) <= v ?
+__device__ __forceinline__ bool bins_le(const float* __restrict__ row, int lo, int hi, float v) {
+    lo = max(lo, 0); hi = min(hi, AID_NBINS - 1);
+    bool ok = true;
+    for (int b = lo; b <= hi; b++) ok &= __ldg(row + b) <= v;
+    return ok;
+}
 
-    float* dst = sm.ring[row % kRing];
+// The window bins of (row, f) that lie outside the whole groups, tested exactly against v.
+// i = f & 15, g = f >> 4. Whole groups inside the window: g-2..g+2, plus g-3 if i <= 3, plus g+3 if i >= 12.
+__device__ __forceinline__ bool edges_le(const float* __restrict__ row, int f, float v) {
+    const int i = f & 15, g = f >> 4;
+    const int left_hi = 16 * (i <= 3 ? g - 3 : g - 2) - 1;
+    const int right_lo = 16 * (i >= 12 ? g + 4 : g + 3);
+    return bins_le(row, f - kHalfF, left_hi, v) && bins_le(row, right_lo, f + kHalfF, v);
+}
+
+__device__ __forceinline__ void push_peak(Smem& sm, uint32_t e) {
+    const int p = atomicAdd(&sm.npeaks, 1);
+    if (p < AID_PEAK_BLOCK_CAP) sm.peaks[p] = e;
+}
+
+// One warp, one row already in registers: A, C5 into the rings; group candidates into q1[qsel].
+__device__ __forceinline__ void row_pass(Smem& sm, const float4 (&x)[4], int row, bool store, bool emit, int qsel, int lane) {
+    const float v[16] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w,
+                         x[2].x, x[2].y, x[2].z, x[2].w, x[3].x, x[3].y, x[3].z, x[3].w};
+    float A = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) A = fmaxf(A, v[i]);
+    // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
+    const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
+    const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
+    const float c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
+    if (store) {
+        const int slot = row % kRing;
+        sm.A[lane * kRingStride + slot] = A;
+        sm.C5[lane * kRingStride + slot] = c5;
+    }
     uint32_t mask = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        float m1[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int i = 4 * q + c;
-            // window of bin 16*lane + i is [16*lane + i - 51, 16*lane + i + 51]
-            const float L = i >= 3 ? __shfl_up_sync(AID_FULL_MASK, suf[i - 3], 3) : __shfl_up_sync(AID_FULL_MASK, suf[i + 13], 4);
-            const float R = i <= 12 ? __shfl_down_sync(AID_FULL_MASK, pre[i + 3], 3) : __shfl_down_sync(AID_FULL_MASK, pre[i - 13], 4);
-            m1[c] = fmaxf(i < 3 ? c5l : (i > 12 ? c5r : c5), fmaxf(L, R));
-            mask |= (v[i] == m1[c] && v[i] > AID_PEAK_MIN_S) ? (1u << i) : 0u;
-        }
-        if (store) *reinterpret_cast<float4*>(dst + 128 * q + 4 * lane) = make_float4(m1[0], m1[1], m1[2], m1[3]);
-    }
+    for (int i = 0; i < 16; i++) mask |= v[i] == A ? (1u << i) : 0u;
     if (lane == 0) mask &= ~((1u << AID_PEAK_MIN_BIN) - 1u);
-    if (!emit) mask = 0;
+    if (!(emit && A == c5 && A > AID_PEAK_MIN_S)) mask = 0;
     if (!__any_sync(AID_FULL_MASK, mask != 0)) return;
     const int cnt = __popc(mask);
     int incl = cnt;
@@ -94,71 +101,101 @@ __device__ __forceinline__ void row_pass(Smem& sm, const float* __restrict__ sro
     const int kept = min(total, AID_ROW_CAND_CAP);
     int base = 0;
     if (lane == 0) {
-        base = atomicAdd(&sm.qn[qsel], kept);
-        if (total > AID_ROW_CAND_CAP) sm.fail = 1;
+        base = atomicAdd(&sm.n1[qsel], kept);
+        if (total > AID_ROW_CAND_CAP) sm.fail = 1;       // capacity rule of aid_params.h: the track fails
     }
     base = __shfl_sync(AID_FULL_MASK, base, 0);
     int pos = incl - cnt;
-    while (mask) {
+    for (; mask; mask &= mask - 1, pos++) {
         const int i = __ffs(mask) - 1;
-        mask &= mask - 1;
-        if (pos < kept && base + pos < kQueue) sm.queue[qsel][base + pos] = ((uint32_t)row << AID_PEAK_F_BITS) | (uint32_t)(16 * lane + i);
-        pos++;
+        if (pos < kept) sm.q1[qsel][base + pos] = ((uint32_t)row << AID_PEAK_F_BITS) | (uint32_t)(16 * lane + i);
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)
 k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
         uint32_t* __restrict__ slots, uint32_t* __restrict__ unit_count, int32_t* __restrict__ track_status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ Smem sm;
     const aid_peak_unit u = units[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = u.n_frames;
     const int row_end = u.row0 + u.n_rows;
-    const int lo = max(0, u.row0 - AID_PEAK_HALF_T);
-    const int hi = min(T, row_end + AID_PEAK_HALF_T);
+    const int lo = max(0, u.row0 - kHalfT);
+    const int hi = min(T, row_end + kHalfT);
     const float* base = spec + u.spec_row0 * AID_NBINS;
 
-    if (tid == 0) { sm.fail = 0; sm.qn[0] = 0; sm.qn[1] = 0; sm.npeaks = 0; }
+    if (tid == 0) { sm.fail = 0; sm.n1[0] = 0; sm.n1[1] = 0; sm.n2 = 0; sm.npeaks = 0; }
     __syncthreads();
 
     int par = 0;
-    for (int step = lo; step < hi; step += kWarps, par ^= 1) {
-        const int r = step + warp;
-        const int rr = min(r, hi - 1);                       // every warp runs the pass; surplus warps redo the last row
-        row_pass(sm, base + (int64_t)rr * AID_NBINS, rr, r < hi, r >= u.row0 && r < row_end, par, lane);
+    for (int step = lo; step < hi; step += kStep, par ^= 1) {
+        // ---- row pass: rows step+warp and step+warp+8; surplus warps redo the last row without side effects
+        const int r0 = step + warp, r1 = r0 + kWarps;
+        const int rr0 = min(r0, hi - 1), rr1 = min(r1, hi - 1);
+        float4 x0[4], x1[4];
+        {
+            const float4* s0 = reinterpret_cast<const float4*>(base + (int64_t)rr0 * AID_NBINS) + lane * 4;
+            const float4* s1 = reinterpret_cast<const float4*>(base + (int64_t)rr1 * AID_NBINS) + lane * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++) x0[q] = __ldg(s0 + q);
+#pragma unroll
+            for (int q = 0; q < 4; q++) x1[q] = __ldg(s1 + q);
+        }
+        row_pass(sm, x0, rr0, r0 < hi, r0 >= u.row0 && r0 < row_end, par, lane);
+        row_pass(sm, x1, rr1, r1 < hi, r1 >= u.row0 && r1 < row_end, par, lane);
         __syncthreads();
-        const int done = min(step + kWarps, hi);
-        const int vhi = done == hi ? row_end : min(row_end, done - AID_PEAK_HALF_T);   // rows < vhi have their full window
-        const int nq = min(sm.qn[par], kQueue);
+        const int done = min(step + kStep, hi);
+        const int vhi = done == hi ? row_end : min(row_end, done - kHalfT);   // rows < vhi have their full window
+
+        // ---- column pass 1: whole groups on all rows of the window, from the rings
+        const int nq = sm.n1[par];
         for (int k = tid; k < nq; k += kThreads) {
-            const uint32_t e = sm.queue[par][k];
-            const int row = (int)(e >> AID_PEAK_F_BITS);
+            const uint32_t e = sm.q1[par][k];
+            const int row = (int)(e >> AID_PEAK_F_BITS), f = (int)(e & (AID_NBINS - 1));
             if (row >= vhi) {                                 // window not complete yet: look again next step
-                const int p = atomicAdd(&sm.qn[par ^ 1], 1);
-                if (p < kQueue) sm.queue[par ^ 1][p] = e;
+                sm.q1[par ^ 1][atomicAdd(&sm.n1[par ^ 1], 1)] = e;
                 continue;
             }
-            const int pf = phys((int)(e & (AID_NBINS - 1)));
+            const int g = f >> 4, i = f & 15;
             const int s0 = row % kRing;
-            const float v = sm.ring[s0][pf];
-            const int dlo = max(-AID_PEAK_HALF_T, -row), dhi = min(AID_PEAK_HALF_T, T - 1 - row);
-            int s = s0 - AID_PEAK_HALF_T;
+            const float v = sm.A[g * kRingStride + s0];
+            const int gx = i <= 3 ? g - 3 : (i >= 12 ? g + 3 : -1);     // the one extra whole group, if any
+            const bool has_x = gx >= 0 && gx < 32;
+            const int dlo = max(-kHalfT, -row), dhi = min(kHalfT, T - 1 - row);
+            int s = s0 - kHalfT;
             if (s < 0) s += kRing;
             float m = -1.0f;
 #pragma unroll
-            for (int d = -AID_PEAK_HALF_T; d <= AID_PEAK_HALF_T; d++) {
-                if (d != 0 && d >= dlo && d <= dhi) m = fmaxf(m, sm.ring[s][pf]);
+            for (int d = -kHalfT; d <= kHalfT; d++) {
+                if (d >= dlo && d <= dhi) {
+                    if (d != 0) m = fmaxf(m, sm.C5[g * kRingStride + s]);
+                    if (has_x) m = fmaxf(m, sm.A[gx * kRingStride + s]);
+                }
                 s = s + 1 == kRing ? 0 : s + 1;
             }
-            if (m <= v) {
-                const int p = atomicAdd(&sm.npeaks, 1);
-                if (p < AID_PEAK_BLOCK_CAP) sm.peaks[p] = e;
-            }
+            if (m > v) continue;
+            const int p = atomicAdd(&sm.n2, 1);
+            if (p < kQ2) { sm.q2[p] = e; continue; }
+            // survivor queue full (degenerate input): settle this one here, serially
+            bool ok = true;
+            for (int d = dlo; d <= dhi && ok; d++) ok = edges_le(base + (int64_t)(row + d) * AID_NBINS, f, v);
+            if (ok) push_peak(sm, e);
         }
         __syncthreads();
-        if (tid == 0) sm.qn[par] = 0;                        // next use of this queue is two steps away
+
+        // ---- column pass 2: one warp per survivor, one lane per row of the window, exact test of the edge bins
+        const int n2 = min(sm.n2, kQ2);
+        for (int k = warp; k < n2; k += kWarps) {
+            const uint32_t e = sm.q2[k];
+            const int row = (int)(e >> AID_PEAK_F_BITS), f = (int)(e & (AID_NBINS - 1));
+            const float v = sm.A[(f >> 4) * kRingStride + row % kRing];
+            const int rw = row - kHalfT + lane;
+            bool ok = true;
+            if (lane <= 2 * kHalfT && rw >= 0 && rw < T) ok = edges_le(base + (int64_t)rw * AID_NBINS, f, v);
+            if (__all_sync(AID_FULL_MASK, ok) && lane == 0) push_peak(sm, e);
+        }
+        __syncthreads();
+        if (tid == 0) { sm.n1[par] = 0; sm.n2 = 0; }         // q1[par] is next written two steps from now
     }
     __syncthreads();
 
@@ -208,15 +245,7 @@ cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, 
                              uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
                              cudaStream_t st) {
     if (n_units <= 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_peaks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    k_peaks<<<n_units, kThreads, sizeof(Smem), st>>>(d_spec, d_units, d_slots, d_unit_count, d_track_status);
+    k_peaks<<<n_units, kThreads, 0, st>>>(d_spec, d_units, d_slots, d_unit_count, d_track_status);
     return cudaGetLastError();
 }
 

@@ -134,8 +134,30 @@ static void sliding_max(const float *in, float *out, int64_t n, int64_t stride, 
     }
 }
 
+/* Number of "group candidates" of one frame (capacity rule of aid_params.h). */
+static int row_group_candidates(const float *row) {
+    float gmax[NB / AID_GROUP_BINS];
+    const int ng = NB / AID_GROUP_BINS;
+    for (int g = 0; g < ng; g++) {
+        float m = row[g * AID_GROUP_BINS];
+        for (int i = 1; i < AID_GROUP_BINS; i++) if (row[g * AID_GROUP_BINS + i] > m) m = row[g * AID_GROUP_BINS + i];
+        gmax[g] = m;
+    }
+    int n = 0;
+    for (int g = 0; g < ng; g++) {
+        int top = gmax[g] > AID_PEAK_MIN_S;
+        for (int d = -2; d <= 2 && top; d++) if (g + d >= 0 && g + d < ng && gmax[g + d] > gmax[g]) top = 0;
+        if (!top) continue;
+        for (int i = 0; i < AID_GROUP_BINS; i++) {
+            int f = g * AID_GROUP_BINS + i;
+            if (f >= AID_PEAK_MIN_BIN && row[f] == gmax[g]) n++;
+        }
+    }
+    return n;
+}
+
 /* S[T][512] -> keys[] = (t << 9) | f in (t, f) order. Returns the peak count, or -1 if a
- * capacity rule of aid_params.h is broken (row candidates > AID_ROW_CAND_CAP, or peaks in an
+ * capacity rule of aid_params.h is broken (group candidates of a frame > AID_ROW_CAND_CAP, or peaks in an
  * aligned 256-frame block > AID_PEAK_BLOCK_CAP). keys must hold AID_PEAK_CAP(T) entries. */
 int64_t aid_oracle_peaks(const float *S, int64_t T, uint32_t *keys) {
     if (T <= 0) return 0;
@@ -146,13 +168,11 @@ int64_t aid_oracle_peaks(const float *S, int64_t T, uint32_t *keys) {
     for (int f = 0; f < NB; f++) sliding_max(m1 + f, m2 + f, T, NB, AID_PEAK_HALF_T, dq);
     int64_t n = 0, in_block = 0;
     for (int64_t t = 0; t < T && n >= 0; t++) {
-        int row_cand = 0;
         if (t % AID_PEAK_BLOCK_FRAMES == 0) in_block = 0;
+        if (row_group_candidates(S + t * NB) > AID_ROW_CAND_CAP) { n = -1; break; }
         for (int f = AID_PEAK_MIN_BIN; f < NB; f++) {
             float v = S[t * NB + f];
-            if (!(v > AID_PEAK_MIN_S) || v != m1[t * NB + f]) continue;
-            if (++row_cand > AID_ROW_CAND_CAP) { n = -1; break; }
-            if (v == m2[t * NB + f]) {
+            if (v > AID_PEAK_MIN_S && v == m2[t * NB + f]) {
                 if (++in_block > AID_PEAK_BLOCK_CAP) { n = -1; break; }
                 keys[n++] = ((uint32_t)t << AID_PEAK_F_BITS) | (uint32_t)f;
             }
