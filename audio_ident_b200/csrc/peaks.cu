@@ -28,7 +28,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kStep = 2 * kWarps;           // rows per step
-constexpr int kRing = 56;                   // rows of A / C5 kept (>= 2 * kStep + 24)
+constexpr int kRing = 64;                   // rows of A / C5 kept (>= 2 * kStep + 24; power of two)
 constexpr int kRingStride = kRing + 1;      // [group][row slot], odd stride: conflict-free both ways
 constexpr int kQ1 = (kStep + 12) * AID_ROW_CAND_CAP;   // group candidates waiting for column pass 1
 constexpr int kQ2 = 256;                    // survivors waiting for column pass 2 (overflow is handled inline)
@@ -38,10 +38,11 @@ struct Smem {
     float A[32 * kRingStride];
     float C5[32 * kRingStride];
     uint32_t q1[2][kQ1];
-    uint32_t q2[kQ2];
+    uint32_t q2[2][kQ2];
+    float q2v[2][kQ2];
     uint32_t peaks[AID_PEAK_BLOCK_CAP];
     int n1[2];
-    int n2;
+    int n2[2];
     int npeaks;
     int fail;
 };
@@ -68,6 +69,12 @@ __device__ __forceinline__ void push_peak(Smem& sm, uint32_t e) {
     if (p < AID_PEAK_BLOCK_CAP) sm.peaks[p] = e;
 }
 
+__device__ __forceinline__ void load_row(float4 (&x)[4], const float* __restrict__ srow, int lane) {
+    const float4* s = reinterpret_cast<const float4*>(srow) + lane * 4;
+#pragma unroll
+    for (int q = 0; q < 4; q++) x[q] = __ldg(s + q);
+}
+
 // One warp, one row already in registers: A, C5 into the rings; group candidates into q1[qsel].
 __device__ __forceinline__ void row_pass(Smem& sm, const float4 (&x)[4], int row, bool store, bool emit, int qsel, int lane) {
     const float v[16] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w,
@@ -80,39 +87,40 @@ __device__ __forceinline__ void row_pass(Smem& sm, const float4 (&x)[4], int row
     const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
     const float c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
     if (store) {
-        const int slot = row % kRing;
+        const int slot = row & (kRing - 1);
         sm.A[lane * kRingStride + slot] = A;
         sm.C5[lane * kRingStride + slot] = c5;
     }
+    const bool cand = emit && A == c5 && A > AID_PEAK_MIN_S;
+    if (!__any_sync(AID_FULL_MASK, cand)) return;
     uint32_t mask = 0;
+    if (cand) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) mask |= v[i] == A ? (1u << i) : 0u;
-    if (lane == 0) mask &= ~((1u << AID_PEAK_MIN_BIN) - 1u);
-    if (!(emit && A == c5 && A > AID_PEAK_MIN_S)) mask = 0;
-    if (!__any_sync(AID_FULL_MASK, mask != 0)) return;
-    const int cnt = __popc(mask);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(AID_FULL_MASK, incl, d);
-        if (lane >= d) incl += o;
+        for (int i = 0; i < 16; i++) mask |= v[i] == A ? (1u << i) : 0u;
+        if (lane == 0) mask &= ~((1u << AID_PEAK_MIN_BIN) - 1u);
     }
-    const int total = __shfl_sync(AID_FULL_MASK, incl, 31);
-    const int kept = min(total, AID_ROW_CAND_CAP);
-    int base = 0;
-    if (lane == 0) {
-        base = atomicAdd(&sm.n1[qsel], kept);
-        if (total > AID_ROW_CAND_CAP) sm.fail = 1;       // capacity rule of aid_params.h: the track fails
+    const int total = __reduce_add_sync(AID_FULL_MASK, __popc(mask));
+    if (total > AID_ROW_CAND_CAP) {                          // capacity rule of aid_params.h: the track fails
+        if (lane == 0) sm.fail = 1;
+        return;
     }
-    base = __shfl_sync(AID_FULL_MASK, base, 0);
-    int pos = incl - cnt;
-    for (; mask; mask &= mask - 1, pos++) {
-        const int i = __ffs(mask) - 1;
-        if (pos < kept) sm.q1[qsel][base + pos] = ((uint32_t)row << AID_PEAK_F_BITS) | (uint32_t)(16 * lane + i);
+    if (mask) {
+        int pos = atomicAdd(&sm.n1[qsel], __popc(mask));
+        for (; mask; mask &= mask - 1, pos++)
+            sm.q1[qsel][pos] = ((uint32_t)row << AID_PEAK_F_BITS) | (uint32_t)(16 * lane + __ffs(mask) - 1);
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
+// column pass 2 for one survivor: one lane per row of the window, exact test of the bins outside the whole groups
+__device__ __forceinline__ void settle_survivor(Smem& sm, const float* __restrict__ base, int T, uint32_t e, float v, int lane) {
+    const int row = (int)(e >> AID_PEAK_F_BITS), f = (int)(e & (AID_NBINS - 1));
+    const int rw = row - kHalfT + lane;
+    bool ok = true;
+    if (lane <= 2 * kHalfT && rw >= 0 && rw < T) ok = edges_le(base + (int64_t)rw * AID_NBINS, f, v);
+    if (__all_sync(AID_FULL_MASK, ok) && lane == 0) push_peak(sm, e);
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
 k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
         uint32_t* __restrict__ slots, uint32_t* __restrict__ unit_count, int32_t* __restrict__ track_status) {
     __shared__ Smem sm;
@@ -124,30 +132,29 @@ k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
     const int hi = min(T, row_end + kHalfT);
     const float* base = spec + u.spec_row0 * AID_NBINS;
 
-    if (tid == 0) { sm.fail = 0; sm.n1[0] = 0; sm.n1[1] = 0; sm.n2 = 0; sm.npeaks = 0; }
+    if (tid == 0) { sm.fail = 0; sm.n1[0] = 0; sm.n1[1] = 0; sm.n2[0] = 0; sm.n2[1] = 0; sm.npeaks = 0; }
     __syncthreads();
+
+    // rows step+warp and step+warp+8 belong to this warp; surplus warps redo the last row without side effects
+    float4 x0[4], x1[4];
+    load_row(x0, base + (int64_t)min(lo + warp, hi - 1) * AID_NBINS, lane);
+    load_row(x1, base + (int64_t)min(lo + warp + kWarps, hi - 1) * AID_NBINS, lane);
 
     int par = 0;
     for (int step = lo; step < hi; step += kStep, par ^= 1) {
-        // ---- row pass: rows step+warp and step+warp+8; surplus warps redo the last row without side effects
         const int r0 = step + warp, r1 = r0 + kWarps;
-        const int rr0 = min(r0, hi - 1), rr1 = min(r1, hi - 1);
-        float4 x0[4], x1[4];
-        {
-            const float4* s0 = reinterpret_cast<const float4*>(base + (int64_t)rr0 * AID_NBINS) + lane * 4;
-            const float4* s1 = reinterpret_cast<const float4*>(base + (int64_t)rr1 * AID_NBINS) + lane * 4;
-#pragma unroll
-            for (int q = 0; q < 4; q++) x0[q] = __ldg(s0 + q);
-#pragma unroll
-            for (int q = 0; q < 4; q++) x1[q] = __ldg(s1 + q);
+        row_pass(sm, x0, min(r0, hi - 1), r0 < hi, r0 >= u.row0 && r0 < row_end, par, lane);
+        row_pass(sm, x1, min(r1, hi - 1), r1 < hi, r1 >= u.row0 && r1 < row_end, par, lane);
+        if (step + kStep < hi) {                             // next step's rows fly during the column passes
+            load_row(x0, base + (int64_t)min(r0 + kStep, hi - 1) * AID_NBINS, lane);
+            load_row(x1, base + (int64_t)min(r1 + kStep, hi - 1) * AID_NBINS, lane);
         }
-        row_pass(sm, x0, rr0, r0 < hi, r0 >= u.row0 && r0 < row_end, par, lane);
-        row_pass(sm, x1, rr1, r1 < hi, r1 >= u.row0 && r1 < row_end, par, lane);
         __syncthreads();
         const int done = min(step + kStep, hi);
         const int vhi = done == hi ? row_end : min(row_end, done - kHalfT);   // rows < vhi have their full window
 
-        // ---- column pass 1: whole groups on all rows of the window, from the rings
+        // ---- column pass 1 (one thread per candidate): whole groups on all rows of the window, from the rings.
+        // Rows are clamped into the track, which only repeats rows that are in the window anyway.
         const int nq = sm.n1[par];
         for (int k = tid; k < nq; k += kThreads) {
             const uint32_t e = sm.q1[par][k];
@@ -157,45 +164,36 @@ k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
                 continue;
             }
             const int g = f >> 4, i = f & 15;
-            const int s0 = row % kRing;
-            const float v = sm.A[g * kRingStride + s0];
-            const int gx = i <= 3 ? g - 3 : (i >= 12 ? g + 3 : -1);     // the one extra whole group, if any
-            const bool has_x = gx >= 0 && gx < 32;
-            const int dlo = max(-kHalfT, -row), dhi = min(kHalfT, T - 1 - row);
-            int s = s0 - kHalfT;
-            if (s < 0) s += kRing;
+            int gx = i <= 3 ? g - 3 : (i >= 12 ? g + 3 : g);  // the one extra whole group, if any (else g again)
+            if (gx < 0 || gx > 31) gx = g;
+            const float* c5 = sm.C5 + g * kRingStride;
+            const float* ax = sm.A + gx * kRingStride;
+            const float v = sm.A[g * kRingStride + (row & (kRing - 1))];
             float m = -1.0f;
 #pragma unroll
             for (int d = -kHalfT; d <= kHalfT; d++) {
-                if (d >= dlo && d <= dhi) {
-                    if (d != 0) m = fmaxf(m, sm.C5[g * kRingStride + s]);
-                    if (has_x) m = fmaxf(m, sm.A[gx * kRingStride + s]);
-                }
-                s = s + 1 == kRing ? 0 : s + 1;
+                const int s = min(max(row + d, 0), T - 1) & (kRing - 1);
+                m = fmaxf(m, fmaxf(c5[s], ax[s]));
             }
             if (m > v) continue;
-            const int p = atomicAdd(&sm.n2, 1);
-            if (p < kQ2) { sm.q2[p] = e; continue; }
+            const int p = atomicAdd(&sm.n2[par], 1);
+            if (p < kQ2) { sm.q2[par][p] = e; sm.q2v[par][p] = v; continue; }
             // survivor queue full (degenerate input): settle this one here, serially
             bool ok = true;
-            for (int d = dlo; d <= dhi && ok; d++) ok = edges_le(base + (int64_t)(row + d) * AID_NBINS, f, v);
+            for (int d = max(-kHalfT, -row); d <= min(kHalfT, T - 1 - row) && ok; d++)
+                ok = edges_le(base + (int64_t)(row + d) * AID_NBINS, f, v);
             if (ok) push_peak(sm, e);
         }
+        // ---- column pass 2 for the survivors of the PREVIOUS step (no barrier needed in between), last warps first
+        const int n2 = min(sm.n2[par ^ 1], kQ2);
+        for (int k = kWarps - 1 - warp; k < n2; k += kWarps) settle_survivor(sm, base, T, sm.q2[par ^ 1][k], sm.q2v[par ^ 1][k], lane);
         __syncthreads();
-
-        // ---- column pass 2: one warp per survivor, one lane per row of the window, exact test of the edge bins
-        const int n2 = min(sm.n2, kQ2);
-        for (int k = warp; k < n2; k += kWarps) {
-            const uint32_t e = sm.q2[k];
-            const int row = (int)(e >> AID_PEAK_F_BITS), f = (int)(e & (AID_NBINS - 1));
-            const float v = sm.A[(f >> 4) * kRingStride + row % kRing];
-            const int rw = row - kHalfT + lane;
-            bool ok = true;
-            if (lane <= 2 * kHalfT && rw >= 0 && rw < T) ok = edges_le(base + (int64_t)rw * AID_NBINS, f, v);
-            if (__all_sync(AID_FULL_MASK, ok) && lane == 0) push_peak(sm, e);
-        }
-        __syncthreads();
-        if (tid == 0) { sm.n1[par] = 0; sm.n2 = 0; }         // q1[par] is next written two steps from now
+        if (tid == 0) { sm.n1[par] = 0; sm.n2[par ^ 1] = 0; }
+    }
+    __syncthreads();
+    {   // survivors of the last step
+        const int n2 = min(sm.n2[par ^ 1], kQ2);
+        for (int k = warp; k < n2; k += kWarps) settle_survivor(sm, base, T, sm.q2[par ^ 1][k], sm.q2v[par ^ 1][k], lane);
     }
     __syncthreads();
 
