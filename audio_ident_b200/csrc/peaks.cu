@@ -47,21 +47,23 @@ struct Smem {
     int fail;
 };
 
-// Are all bins of `row` in [lo, hi] (clipped to the spectrogram) <= v ?
-__device__ __forceinline__ bool bins_le(const float* __restrict__ row, int lo, int hi, float v) {
-    lo = max(lo, 0); hi = min(hi, AID_NBINS - 1);
-    bool ok = true;
-    for (int b = lo; b <= hi; b++) ok &= __ldg(row + b) <= v;
-    return ok;
-}
-
 // The window bins of (row, f) that lie outside the whole groups, tested exactly against v.
-// i = f & 15, g = f >> 4. Whole groups inside the window: g-2..g+2, plus g-3 if i <= 3, plus g+3 if i >= 12.
+// i = f & 15, g = f >> 4. Whole groups inside the window: g-2..g+2, plus g-3 if i <= 3, plus g+3 if i >= 12;
+// that leaves at most 15 bins on each side. All loads are issued before the first compare (one L2 round trip).
 __device__ __forceinline__ bool edges_le(const float* __restrict__ row, int f, float v) {
     const int i = f & 15, g = f >> 4;
-    const int left_hi = 16 * (i <= 3 ? g - 3 : g - 2) - 1;
-    const int right_lo = 16 * (i >= 12 ? g + 4 : g + 3);
-    return bins_le(row, f - kHalfF, left_hi, v) && bins_le(row, right_lo, f + kHalfF, v);
+    const int left_lo = max(f - kHalfF, 0), left_hi = 16 * (i <= 3 ? g - 3 : g - 2) - 1;
+    const int right_lo = 16 * (i >= 12 ? g + 4 : g + 3), right_hi = min(f + kHalfF, AID_NBINS - 1);
+    float x[30];
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+        x[k] = left_lo + k <= left_hi ? __ldg(row + left_lo + k) : -1.0f;
+        x[15 + k] = right_lo + k <= right_hi ? __ldg(row + right_lo + k) : -1.0f;
+    }
+    float m = x[0];
+#pragma unroll
+    for (int k = 1; k < 30; k++) m = fmaxf(m, x[k]);
+    return m <= v;
 }
 
 __device__ __forceinline__ void push_peak(Smem& sm, uint32_t e) {
