@@ -74,49 +74,110 @@ def merge_rows(blocks):
 
 class ShardedIdentifier:
     """`backend` is an audio_ident_b200.engine.Engine (or anything with the same index_add / query /
-    query_hashes methods, which is how the CPU gloo tests drive the exchange logic)."""
+    query_hashes methods, which is how the CPU gloo tests drive the exchange logic). With `device` set (a torch
+    CUDA device) row blocks are mapped, exchanged (NCCL) and merged on the GPU."""
 
     def __init__(self, backend, rank: int = 0, world: int = 1, group=None, device=None):
         self.backend, self.rank, self.world, self.group, self.device = backend, rank, world, group, device
         self.to_global: list[int] = []          # local track number -> global track number
+        self._to_global_dev = None
 
     # ---- ingest: no collective
     def my_tracks(self, n_global: int, first: int = 0) -> list[int]:
         return [g for g in range(first, first + n_global) if shard_of(g, self.world) == self.rank]
 
-    def add(self, pcm, sample_off, global_ids: Sequence[int], device: bool = False) -> np.ndarray:
+    def _register(self, global_ids, ok):
         assert all(shard_of(g, self.world) == self.rank for g in global_ids)
         assert not self.to_global or not len(global_ids) or global_ids[0] > self.to_global[-1], "add in increasing global order"
-        ok = self.backend.index_add(pcm, sample_off, [str(g) for g in global_ids], device=device)
         self.to_global.extend(int(g) for g, k in zip(global_ids, ok) if k)      # a refused track gets no local number
+        self._to_global_dev = None
+
+    def add(self, pcm, sample_off, global_ids: Sequence[int], device: bool = False) -> np.ndarray:
+        ok = self.backend.index_add(pcm, sample_off, [str(g) for g in global_ids], device=device)
+        self._register(global_ids, ok)
         return ok
 
     def add_hashes(self, h, t, hash_off, n_frames, global_ids: Sequence[int]) -> np.ndarray:
         ok = self.backend.index_add_hashes(h, t, hash_off, n_frames, [str(g) for g in global_ids])
-        self.to_global.extend(int(g) for g, k in zip(global_ids, ok) if k)
+        self._register(global_ids, ok)
         return ok
 
     # ---- identify: local probe + one all-gather + identical merge everywhere
-    def _exchange(self, local: np.ndarray):
-        """local rows -> [P, n_q, 50, 5]; on a CUDA device the block stays a torch tensor so the merge runs there."""
-        if self.world == 1 and self.device is None:
-            return local[None]
+    def _all_gather(self, t):
         import torch
         import torch.distributed as dist
-        t = torch.from_numpy(np.ascontiguousarray(local))
-        if self.device is not None:
-            t = t.to(self.device, non_blocking=True)
-        if self.world == 1:
-            return t[None]
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)
-        out = out.reshape((self.world,) + tuple(t.shape))
-        return out if self.device is not None else out.numpy()
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out.reshape((self.world,) + tuple(t.shape))
 
-    def query(self, pcm, sample_off, device: bool = False):
-        rows, n = self.backend.query(pcm, sample_off, device=device)
-        return merge_rows(self._exchange(rows_to_array(rows, n, np.asarray(self.to_global, np.int64))))
+    def _merge_local(self, rows: np.ndarray, n: np.ndarray):
+        """this rank's structured rows -> global numbering -> exchange -> merged [n_q, 50, 5], n_rows."""
+        if self.device is None:                                     # CPU path (gloo tests, single process)
+            local = rows_to_array(rows, n, np.asarray(self.to_global, np.int64))
+            if self.world == 1:
+                return merge_rows(local[None])
+            import torch
+            return merge_rows(self._all_gather(torch.from_numpy(local)).numpy())
+        import torch
+        if self._to_global_dev is None:
+            self._to_global_dev = torch.tensor(self.to_global if self.to_global else [0], dtype=torch.int64, device=self.device)
+        n_q = rows.shape[0]
+        raw = torch.from_numpy(rows.view(np.int32).reshape(n_q, rows.shape[1], 5)).to(self.device, non_blocking=True)
+        nn = torch.from_numpy(n).to(self.device, non_blocking=True)
+        blk = torch.full((n_q, MAX_ROWS, 5), -1, dtype=torch.int64, device=self.device)
+        blk[:, :raw.shape[1]] = raw.to(torch.int64)
+        blk[:, :, 1] = self._to_global_dev[(blk[:, :, 1] & 0xFFFFFFFF).clamp_(0, len(self._to_global_dev) - 1)]
+        valid = torch.arange(MAX_ROWS, device=self.device)[None, :] < nn[:, None]
+        blk = torch.where(valid[:, :, None], blk, torch.full_like(blk, -1))
+        if self.world == 1:
+            return merge_rows(blk[None])
+        return merge_rows(self._all_gather(blk))
+
+    def query(self, pcm, sample_off, device: bool = False, split_fingerprint: bool = True):
+        """Every rank passes the same query batch. With several ranks the fingerprinting itself is split (rank r
+        fingerprints windows [r*n/P, (r+1)*n/P), hashes are all-gathered) so that no stage is replicated."""
+        sample_off = np.ascontiguousarray(sample_off, np.int64)
+        n = len(sample_off) - 1
+        if self.world == 1 or not split_fingerprint or n < self.world:
+            rows, nr = self.backend.query(pcm, sample_off, device=device)
+            return self._merge_local(rows, nr)
+        import torch
+        lo, hi = self.rank * n // self.world, (self.rank + 1) * n // self.world
+        sub_off = sample_off[lo:hi + 1]
+        if device:
+            res = self.backend.fingerprint_dev(pcm, sub_off)
+            off32 = self.backend.to_host(res.d_hash_off, hi - lo + 1, np.uint32).astype(np.int64)
+            h = self.backend.to_host(res.d_hash, int(off32[-1]), np.uint32)
+            t = self.backend.to_host(res.d_t_anchor, int(off32[-1]), np.uint32)
+            st = self.backend.to_host(res.d_status, hi - lo, np.int32)
+            keep = (st & 3) == 0
+        else:
+            h, t, off32, st = self.backend.fingerprint(pcm, sub_off)
+            keep = np.ones(hi - lo, bool)
+        cnt = np.where(keep, np.diff(off32), 0)
+        if not keep.all():
+            sel = np.concatenate([np.arange(off32[i], off32[i + 1]) for i in range(hi - lo) if keep[i]]) if keep.any() else np.zeros(0, np.int64)
+            h, t = h[sel], t[sel]
+        # all-gather window counts (fixed size), then the hashes padded to the largest rank
+        dev = self.device if self.device is not None else "cpu"
+        per = (n + self.world - 1) // self.world + 1
+        c = torch.zeros(per, dtype=torch.int64, device=dev); c[:hi - lo] = torch.from_numpy(cnt).to(dev)
+        counts = self._all_gather(c)                                       # [P, per]
+        totals = counts.sum(dim=1)
+        cap = int(totals.max().item())
+        buf = torch.zeros((2, max(cap, 1)), dtype=torch.int64, device=dev)
+        buf[0, :len(h)] = torch.from_numpy(h.astype(np.int64)).to(dev)
+        buf[1, :len(t)] = torch.from_numpy(t.astype(np.int64)).to(dev)
+        allb = self._all_gather(buf).cpu().numpy()                         # [P, 2, cap]
+        counts = counts.cpu().numpy(); totals = totals.cpu().numpy()
+        hs, ts, lens = [], [], []
+        for r in range(self.world):
+            nr_ = (r + 1) * n // self.world - r * n // self.world
+            hs.append(allb[r, 0, :totals[r]]); ts.append(allb[r, 1, :totals[r]]); lens.append(counts[r, :nr_])
+        off = np.concatenate([[0], np.cumsum(np.concatenate(lens))])
+        rows, nr = self.backend.query_hashes(np.concatenate(hs).astype(np.uint32), np.concatenate(ts).astype(np.uint32), off)
+        return self._merge_local(rows, nr)
 
     def query_hashes(self, h, t, hash_off):
         rows, n = self.backend.query_hashes(h, t, hash_off)
-        return merge_rows(self._exchange(rows_to_array(rows, n, np.asarray(self.to_global, np.int64))))
+        return self._merge_local(rows, n)

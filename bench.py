@@ -111,11 +111,12 @@ def run_reference(args, rank):
     pcm = sample_tracks(args, n, samples)
     off = np.arange(n + 1, dtype=np.int64) * samples
     used = 0
+    threads = len(os.sched_getaffinity(0))      # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(args.warmup):
-        used = oracle.fingerprint_batch(pcm, off)[5]
+        used = oracle.fingerprint_batch(pcm, off, threads)[5]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        used = oracle.fingerprint_batch(pcm, off)[5]
+        used = oracle.fingerprint_batch(pcm, off, threads)[5]
     dt = (time.perf_counter() - t0) / args.steps
     hours = n * args.seconds / 3600.0
     v = hours / dt
@@ -317,9 +318,10 @@ def main():
         nc = min(nc, n)
         pcm_s = d_pcm[:nc * samples].cpu().numpy()
         off_s = np.arange(nc + 1, dtype=np.int64) * samples
-        oracle.fingerprint_batch(pcm_s[:2 * samples], off_s[:3])
+        threads = len(os.sched_getaffinity(0))
+        oracle.fingerprint_batch(pcm_s[:2 * samples], off_s[:3], threads)
         t0 = time.perf_counter()
-        rh, rt, roff, rnh, rnp, used = oracle.fingerprint_batch(pcm_s, off_s)
+        rh, rt, roff, rnh, rnp, used = oracle.fingerprint_batch(pcm_s, off_s, threads)
         dt = time.perf_counter() - t0
         cpu = {"value": (nc * args.seconds / 3600.0) / dt, "unit": UNIT, "cores": int(used), "kind": "port",
                "sample": f"first {nc} of the {n} tracks, one pass, {dt:.1f} s of wall time",

@@ -32,6 +32,16 @@ class OracleBackend:
             self.tr.append(np.full(b - a, self.n, np.uint32)); self.n += 1
         return np.ones(len(names), bool)
 
+    def fingerprint(self, pcm, sample_off):
+        from oracle import oracle
+        sample_off = np.asarray(sample_off, np.int64)
+        h, t, off, nh, npk, used = oracle.fingerprint_batch(np.asarray(pcm, np.float32)[sample_off[0]:], sample_off - sample_off[0], 1)
+        return h, t, off, np.zeros(len(sample_off) - 1, np.int32)
+
+    def query(self, pcm, sample_off, device=False):
+        h, t, off, _ = self.fingerprint(pcm, sample_off)
+        return self.query_hashes(h, t, off)
+
     def query_hashes(self, h, t, hash_off):
         from oracle import oracle
         ix = oracle.Index(np.concatenate(self.h), np.concatenate(self.tr), np.concatenate(self.t))
@@ -71,6 +81,43 @@ def worker(rank, world, port, q):
     q.put((rank, merged, n))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def pcm_worker(rank, world, port, q):
+    """queries given as PCM: rank r fingerprints its slice of the windows, hashes are all-gathered (split path)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from audio_ident_b200 import synth
+    from oracle import oracle
+    tracks = [synth.make_track(900 + k, 6.0) for k in range(6)]
+    sh = sharded.ShardedIdentifier(OracleBackend(), rank, world)
+    for g in sh.my_tracks(len(tracks)):
+        h, t = oracle.fingerprint(tracks[g])
+        sh.add_hashes(h, t, [0, len(h)], [oracle.num_frames(len(tracks[g]))], [g])
+    wins = [tracks[k % 6][8000 * (k % 3):8000 * (k % 3) + 56000] for k in range(7)]      # 7 windows: uneven split
+    pcm = np.concatenate(wins); off = np.concatenate([[0], np.cumsum([len(w) for w in wins])])
+    a = sh.query(pcm, off, split_fingerprint=True)
+    b = sh.query(pcm, off, split_fingerprint=False)
+    q.put((rank, a, b))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_split_fingerprinting_equals_replicated(oracle):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=pcm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, a, b in results:
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert (a[1] >= 1).all() and [int(a[0][k, 0, 1]) for k in range(7)] == [k % 6 for k in range(7)]
+    assert np.array_equal(results[0][1][0], results[1][1][0])
 
 
 def free_port():
