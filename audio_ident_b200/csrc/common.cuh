@@ -26,6 +26,12 @@ struct aid_peak_unit {     // one CTA: output rows [row0, row0 + n_rows) of one 
     int32_t n_rows;
 };
 
+struct aid_peak_run {      // one warp of the peak kernel: `n_blocks` consecutive peak units (256-frame blocks) of one track
+    int32_t first_unit;
+    int32_t n_blocks;
+};
+
+#define AID_PEAK_RUN_BLOCKS    4       // blocks streamed back to back by one warp (halo re-read: 24 rows per run)
 #define AID_STFT_UNIT_FRAMES   64      // frames per warp-unit (even)
 #define AID_PEAK_BLOCK_FRAMES  256     // must equal the spec's aligned block (aid_params.h)
 
@@ -38,8 +44,8 @@ struct aid_tables {              // device-resident constant tables, built once 
 cudaError_t aid_launch_stft(const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
                             int n_units, float* d_spec, cudaStream_t st);
 
-cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, int n_units,
-                             uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
+cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, const aid_peak_run* d_runs,
+                             int n_runs, uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
                              cudaStream_t st);
 
 cudaError_t aid_launch_peak_compact(const uint32_t* d_slots, const uint32_t* d_unit_count,

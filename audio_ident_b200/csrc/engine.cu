@@ -138,6 +138,14 @@ int aid_build_plan(const int64_t* sample_off, int first, int count, int64_t fram
     plan.host_status.assign(count, AID_TRACK_OK);
     plan.first_punit.assign(count + 1, 0);
     const int64_t base = sample_off[first];
+    // blocks streamed back to back by one warp of the peak kernel: longer runs re-read fewer halo rows, but the
+    // launch needs several waves of warps (148 SMs x 12 resident warps) to balance
+    int64_t all_blocks = 0;
+    for (int i = 0; i < count; i++) {
+        const int64_t T = aid_num_frames(sample_off[first + i + 1] - sample_off[first + i]);
+        if (T <= frame_limit) all_blocks += (T + AID_PEAK_BLOCK_FRAMES - 1) / AID_PEAK_BLOCK_FRAMES;
+    }
+    const int64_t run_blocks = std::max<int64_t>(1, std::min<int64_t>(AID_PEAK_RUN_BLOCKS, all_blocks / (8 * 148 * 12)));
     for (int i = 0; i < count; i++) {
         const int64_t begin = sample_off[first + i], end = sample_off[first + i + 1];
         if (end < begin) return AID_E_ARG;
@@ -156,6 +164,13 @@ int aid_build_plan(const int64_t* sample_off, int first, int count, int64_t fram
             plan.sunits.push_back(u);
         }
         plan.first_punit[i] = (uint32_t)plan.punits.size();
+        for (int64_t r0 = 0; r0 < T; r0 += AID_PEAK_BLOCK_FRAMES * run_blocks) {
+            aid_peak_run run;
+            const int64_t blocks_left = (T - r0 + AID_PEAK_BLOCK_FRAMES - 1) / AID_PEAK_BLOCK_FRAMES;
+            run.n_blocks = (int32_t)std::min<int64_t>(run_blocks, blocks_left);
+            run.first_unit = (int32_t)(plan.first_punit[i] + r0 / AID_PEAK_BLOCK_FRAMES);
+            plan.pruns.push_back(run);
+        }
         for (int64_t r0 = 0; r0 < T; r0 += AID_PEAK_BLOCK_FRAMES) {
             aid_peak_unit u;
             u.spec_row0 = plan.frame_off[i];
@@ -195,12 +210,14 @@ int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, in
     const size_t b0 = align256(plan.sunits.size() * sizeof(aid_stft_unit));
     const size_t b1 = align256(nu * sizeof(aid_peak_unit));
     const size_t b2 = align256((n + 1) * sizeof(uint32_t));
-    AID_CUDA(e, s.desc.ensure(b0 + b1 + b2 + 256));
-    AID_CUDA(e, s.h_desc.ensure(b0 + b1 + b2 + 256));
+    const size_t b3 = align256(plan.pruns.size() * sizeof(aid_peak_run));
+    AID_CUDA(e, s.desc.ensure(b0 + b1 + b2 + b3 + 256));
+    AID_CUDA(e, s.h_desc.ensure(b0 + b1 + b2 + b3 + 256));
     AID_CUDA(e, s.h_small.ensure((n + 1) * (sizeof(uint32_t) + sizeof(int32_t)) + 1024));
     s.d_sunits = reinterpret_cast<aid_stft_unit*>(s.desc.as<char>());
     s.d_punits = reinterpret_cast<aid_peak_unit*>(s.desc.as<char>() + b0);
     s.d_first_punit = reinterpret_cast<uint32_t*>(s.desc.as<char>() + b0 + b1);
+    s.d_pruns = reinterpret_cast<aid_peak_run*>(s.desc.as<char>() + b0 + b1 + b2);
     return AID_OK;
 }
 
@@ -232,12 +249,14 @@ int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d
     char* h = s.h_desc.as<char>();
     const size_t b0 = (size_t)((char*)s.d_punits - (char*)s.d_sunits);
     const size_t b1 = (size_t)((char*)s.d_first_punit - (char*)s.d_punits);
-    const size_t b2 = (size_t)(n + 1) * sizeof(uint32_t);
+    const size_t b2 = (size_t)((char*)s.d_pruns - (char*)s.d_first_punit);
+    const size_t b3 = plan.pruns.size() * sizeof(aid_peak_run);
     AID_CUDA(e, cudaEventSynchronize(s.done));      // the previous upload from this staging buffer has landed
     if (nsu) memcpy(h, plan.sunits.data(), (size_t)nsu * sizeof(aid_stft_unit));
     if (npu) memcpy(h + b0, plan.punits.data(), (size_t)npu * sizeof(aid_peak_unit));
-    memcpy(h + b0 + b1, plan.first_punit.data(), b2);
-    AID_CUDA(e, cudaMemcpyAsync(s.desc.p, h, b0 + b1 + b2, cudaMemcpyHostToDevice, st));
+    memcpy(h + b0 + b1, plan.first_punit.data(), (size_t)(n + 1) * sizeof(uint32_t));
+    if (b3) memcpy(h + b0 + b1 + b2, plan.pruns.data(), b3);
+    AID_CUDA(e, cudaMemcpyAsync(s.desc.p, h, b0 + b1 + b2 + b3, cudaMemcpyHostToDevice, st));
     AID_CUDA(e, cudaEventRecord(s.done, st));
     AID_CUDA(e, cudaMemsetAsync(s.status.p, 0, (size_t)(n + 1) * sizeof(int32_t), st));
     AID_CUDA(e, cudaMemsetAsync(s.misc.p, 0, 256, st));
@@ -248,8 +267,8 @@ int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d
     { StageTimer tm(e, st, 0);
       AID_CUDA(e, aid_launch_stft(e->tables, d_pcm, s.d_sunits, nsu, s.spec.as<float>(), st)); }
     { StageTimer tm(e, st, 1);
-      AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, npu, s.slots.as<uint32_t>(), unit_cnt,
-                                   s.status.as<int32_t>(), st)); }
+      AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, s.d_pruns, (int)plan.pruns.size(),
+                                   s.slots.as<uint32_t>(), unit_cnt, s.status.as<int32_t>(), st)); }
     // unit counts -> dense positions (unit_pos[npu] = total peaks)
     { StageTimer tm2(e, st, 2);
     AID_CUDA(e, cudaMemsetAsync(unit_cnt + npu, 0, sizeof(uint32_t), st));
@@ -472,10 +491,11 @@ extern "C" int aid_peaks_host(aid_engine* e, const float* spec, const int64_t* f
     AID_CUDA(e, cudaMemcpyAsync(s.spec.p, spec, (size_t)plan.total_frames * AID_NBINS * sizeof(float), cudaMemcpyHostToDevice, s.st));
     AID_CUDA(e, cudaMemcpyAsync(s.d_punits, plan.punits.data(), (size_t)npu * sizeof(aid_peak_unit), cudaMemcpyHostToDevice, s.st));
     AID_CUDA(e, cudaMemcpyAsync(s.d_first_punit, plan.first_punit.data(), (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.st));
+    AID_CUDA(e, cudaMemcpyAsync(s.d_pruns, plan.pruns.data(), plan.pruns.size() * sizeof(aid_peak_run), cudaMemcpyHostToDevice, s.st));
     AID_CUDA(e, cudaMemsetAsync(s.status.p, 0, (size_t)(n + 1) * sizeof(int32_t), s.st));
     uint32_t* unit_cnt = s.unit_pos.as<uint32_t>();
     uint32_t* unit_pos = unit_cnt + (npu + 1);
-    AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, npu, s.slots.as<uint32_t>(), unit_cnt, s.status.as<int32_t>(), s.st));
+    AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, s.d_pruns, (int)plan.pruns.size(), s.slots.as<uint32_t>(), unit_cnt, s.status.as<int32_t>(), s.st));
     AID_CUDA(e, cudaMemsetAsync(unit_cnt + npu, 0, sizeof(uint32_t), s.st));
     AID_CUDA(e, aid_launch_scan_u32(unit_cnt, unit_pos, npu + 1, s.scan_tmp.as<uint32_t>(), nullptr, nullptr, s.st));
     AID_CUDA(e, aid_launch_peak_compact(s.slots.as<uint32_t>(), unit_cnt, unit_pos, s.d_punits, npu, s.peaks.as<uint32_t>(), s.peak_track.as<uint32_t>(), s.st));

@@ -46,6 +46,7 @@ struct Plan {
     std::vector<int32_t> host_status;   // AID_TRACK_EMPTY / AID_TRACK_TOO_LONG
     std::vector<aid_stft_unit> sunits;
     std::vector<aid_peak_unit> punits;
+    std::vector<aid_peak_run> pruns;
     std::vector<uint32_t> first_punit;  // [n+1]
     int64_t total_frames = 0;
     int64_t peak_cap = 0;               // n_punits * AID_PEAK_BLOCK_CAP
@@ -62,6 +63,7 @@ struct Slot {
     // views into `desc` (one upload per sub-batch)
     aid_stft_unit* d_sunits = nullptr;
     aid_peak_unit* d_punits = nullptr;
+    aid_peak_run* d_pruns = nullptr;
     uint32_t* d_first_punit = nullptr;
     void release();
 };
@@ -72,7 +74,7 @@ struct aid_engine {
     int device = 0;
     std::string err;
     int64_t launches = 0;
-    int64_t max_batch_frames = 2 * 1024 * 1024;
+    int64_t max_batch_frames = 8 * 1024 * 1024;
     Slot slot[2];
     DevBuf d_window, d_twiddle;
     aid_tables tables{};

@@ -4,15 +4,15 @@
 // reference audio-ident-service/app/audio/fingerprint.py:117-125). Definition of the result:
 // oracle/aid_oracle.c aid_oracle_peaks(); bit-exact on the same spectrogram.
 //
-// Design (DESIGN.md "Peak kernel"): ONE WARP streams the rows of one aligned 256-frame block of one track
-// plus a 12-row halo on each side; warps never wait for each other (no block barriers). A lane owns one aligned
-// 16-bin group of the row (32 groups = 512 bins) and the warp keeps three tiny rings in shared memory --
+// Design (DESIGN.md "Peak kernel"): ONE WARP streams the rows of a run of up to 4 consecutive aligned 256-frame
+// blocks of one track plus a 12-row halo on each side; warps never wait for each other (no block barriers). A lane owns one aligned
+// 16-bin group of the row (32 groups = 512 bins) and the warp keeps two tiny rings in shared memory --
 // never the spectrogram itself:
 //    A [row][g]   = maximum of group g                       (32 rows x 32 floats)
 //    C5[row][g]   = max(A[g-2 .. g+2])
-//    M [row][g]   = 16-bit mask of the group's points that equal A, pass the gates, and have A == C5
-//                   ("group candidates": a point can only be the maximum of its 103-bin window if it is one,
-//                   because groups g-2..g+2 lie inside every window of group g)
+//    sign of A    = set if A passes the gate and A == C5 ("candidate group": a point can only be the maximum of
+//                   its 103-bin window if it is the maximum of such a group, because groups g-2..g+2 lie inside
+//                   every window of group g)
 //  * Row pass: 4 x LDG.128 per lane (the next row is already in flight), one max-reduction, four shuffles.
 //  * Column pass, 12 rows behind: the maximum of a lane's C5 column over the 25 rows of the window comes from the
 //    van Herk / Gil-Werman decomposition -- a running prefix maximum over the current block of 25 rows (one
@@ -31,14 +31,16 @@
 namespace {
 
 constexpr int kWarpsPerCta = 4;
-constexpr int kRing = 32;                   // rows kept (>= 25: the sweep for row c runs when row c + 12 is in)
-constexpr int kBuf = 128;                   // peaks buffered in shared memory before spilling to the slot list
+constexpr int kRing = 32;                   // rows kept (>= 25: the column pass for row c runs when row c + 12 is in)
+constexpr int kBlock = 2 * AID_PEAK_HALF_T + 1;   // 25: van Herk block = window height
+constexpr int kBuf = 64;                    // peaks buffered in shared memory before spilling to the slot list
 constexpr int kHalfF = AID_PEAK_HALF_F, kHalfT = AID_PEAK_HALF_T;
 
+// Every lane reads and writes only its own column of these rings (lane = group), so they need no warp
+// synchronisation at all; the layout [row][lane] makes every access conflict-free.
 struct WarpSmem {
-    float A[kRing][32];
+    float A[kRing][32];        // group maximum; stored NEGATED when the group is a candidate (S >= 0, so the sign is free)
     float C5[kRing][32];
-    uint16_t M[kRing][32];
     uint32_t buf[kBuf];
 };
 
@@ -67,21 +69,95 @@ __device__ __forceinline__ void load_row(float4 (&x)[4], const float* __restrict
     for (int q = 0; q < 4; q++) x[q] = __ldg(s + q);
 }
 
-struct Stream {             // per-warp state that is the same in every lane
+struct Stream {             // per-warp state (the same in every lane except px)
     const float* base;      // row 0 of the track
     uint32_t* out;          // the unit's slot list in global memory
     int T, lo, hi;          // frames in the track; first / one-past-last row this warp computes
+    int row0, row_end;      // rows whose peaks this warp reports
+    int unit, block_end;    // the peak unit (256-frame block) being filled; first row of the next one
+    int track;
+    uint32_t* unit_count;
+    int32_t* track_status;
     int n_peaks;
-    bool fail;
     int jb;                 // rows of the current 25-row block already in (1..25), counted from lo
     float px;               // per lane: max of C5 over those rows
 };
 
+// Row pass for one row held in registers: group maximum, 5-group maximum, candidate flag -> rings.
+__device__ __forceinline__ void row_pass(WarpSmem& sm, Stream& st, const float4 (&x)[4], int r, int lane) {
+    float A = fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[0].z, x[0].w));
+#pragma unroll
+    for (int q = 1; q < 4; q++) A = fmaxf(A, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
+    // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
+    const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
+    const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
+    const float c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
+    if (st.jb == kBlock) {                                   // the previous 25-row block is complete: turn its C5
+        float sfx = -1.0f;                                   // entries into suffix maxima, start a new block
+#pragma unroll
+        for (int k = 1; k <= kBlock; k++) {
+            const int sl = (r - k) & (kRing - 1);
+            sfx = fmaxf(sfx, sm.C5[sl][lane]);
+            sm.C5[sl][lane] = sfx;
+        }
+        st.jb = 0;
+        st.px = -1.0f;
+    }
+    st.jb++;
+    st.px = fmaxf(st.px, c5);
+    const int slot = r & (kRing - 1);
+    const bool cand = r >= st.row0 && r < st.row_end && A == c5 && A > AID_PEAK_MIN_S;
+    sm.A[slot][lane] = cand ? -A : A;
+    sm.C5[slot][lane] = c5;
+}
+
+// ascending bitonic sort of N (power of two) keys by one warp; `a` is shared or global memory
+__device__ __forceinline__ void warp_sort(uint32_t* a, int N, int lane) {
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < N; i += 32) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint32_t x = a[i], y = a[p];
+                    if ((x > y) == ((i & k) == 0)) { a[i] = y; a[p] = x; }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+// The current block is complete: order its peaks by (t, f), publish its list, move on to the next block.
+__device__ __forceinline__ void flush_block(WarpSmem& sm, Stream& st, int lane) {
+    const int n = min(st.n_peaks, AID_PEAK_BLOCK_CAP);
+    int N = 1;
+    while (N < n) N <<= 1;
+    __syncwarp();
+    if (n <= kBuf) {
+        for (int i = n + lane; i < N; i += 32) sm.buf[i] = 0xffffffffu;
+        __syncwarp();
+        warp_sort(sm.buf, N, lane);
+        for (int i = lane; i < n; i += 32) st.out[i] = sm.buf[i];
+    } else {                                               // degenerate input: finish in the slot list itself
+        for (int i = lane; i < kBuf; i += 32) st.out[i] = sm.buf[i];
+        for (int i = n + lane; i < N; i += 32) st.out[i] = 0xffffffffu;
+        __syncwarp();
+        warp_sort(st.out, N, lane);
+    }
+    if (lane == 0) {
+        st.unit_count[st.unit] = (uint32_t)n;
+        if (st.n_peaks > AID_PEAK_BLOCK_CAP) atomicOr(st.track_status + st.track, AID_TRACK_PEAK_OVERFLOW);
+    }
+    __syncwarp();
+    st.n_peaks = 0;
+    st.unit++;
+    st.block_end += AID_PEAK_BLOCK_FRAMES;
+    st.out += AID_PEAK_BLOCK_CAP;
+}
+
 // Column pass + exact settlement for row c; `last` is the newest row in the rings (c + 12, or hi - 1 at the end
 // of the track). The 25-row block structure is counted from row lo.
 __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int last, int lane) {
-    uint32_t mask = sm.M[c & (kRing - 1)][lane];
-    if (!__any_sync(AID_FULL_MASK, mask != 0)) return;
+    if (c >= st.block_end) flush_block(sm, st, lane);       // rows are verified in order: the previous block is done
     // max of C5 over rows [max(c-12, lo), last]: prefix of the current block, plus the suffix maxima of the previous
     // block from the window's first row on (they were written over the C5 ring when that block was completed)
     const int first = max(c - kHalfT, st.lo);
@@ -92,12 +168,25 @@ __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int 
         mc = -1.0f;                                         // the block; its rows are all in the (raw) current block
         for (int rw = first; rw <= last; rw++) mc = fmaxf(mc, sm.C5[rw & (kRing - 1)][lane]);
     }
-    const float v = sm.A[c & (kRing - 1)][lane];
-    uint32_t keep = (mask && mc <= v) ? mask : 0u;
+    const float av = sm.A[c & (kRing - 1)][lane];
+    const float v = fabsf(av);
+    const bool pass = av < 0.0f && mc <= v;
+    if (!__any_sync(AID_FULL_MASK, pass)) return;           // ~3 rows in 4 end here
+    // which points of the group equal its maximum? (re-read the 16 bins: L1/L2 hit, rare)
+    uint32_t keep = 0;
+    if (pass) {
+        float4 x[4];
+        load_row(x, st.base + (int64_t)c * AID_NBINS, lane);
+        const float w[16] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w,
+                             x[2].x, x[2].y, x[2].z, x[2].w, x[3].x, x[3].y, x[3].z, x[3].w};
+#pragma unroll
+        for (int i = 0; i < 16; i++) keep |= w[i] == v ? (1u << i) : 0u;
+        if (lane == 0) keep &= ~((1u << AID_PEAK_MIN_BIN) - 1u);
+    }
     // points at i <= 3 also need group lane-3, points at i >= 12 also need group lane+3, on every row of the window
     if (__any_sync(AID_FULL_MASK, (keep & 0xf00fu) != 0)) {
         float ma = -1.0f;
-        for (int rw = first; rw <= last; rw++) ma = fmaxf(ma, sm.A[rw & (kRing - 1)][lane]);
+        for (int rw = first; rw <= last; rw++) ma = fmaxf(ma, fabsf(sm.A[rw & (kRing - 1)][lane]));
         // a missing neighbour group returns the lane's own maximum, which is <= mc <= v: harmless
         const float ml = __shfl_up_sync(AID_FULL_MASK, ma, 3), mr = __shfl_down_sync(AID_FULL_MASK, ma, 3);
         keep &= (ml <= v ? 0x000fu : 0u) | 0x0ff0u | (mr <= v ? 0xf000u : 0u);
@@ -125,110 +214,57 @@ __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int 
     }
 }
 
-// ascending bitonic sort of N (power of two) keys by one warp; `a` is shared or global memory
-__device__ __forceinline__ void warp_sort(uint32_t* a, int N, int lane) {
-    for (int k = 2; k <= N; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < N; i += 32) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const uint32_t x = a[i], y = a[p];
-                    if ((x > y) == ((i & k) == 0)) { a[i] = y; a[p] = x; }
-                }
-            }
-            __syncwarp();
-        }
-}
-
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units, int n_units,
-        uint32_t* __restrict__ slots, uint32_t* __restrict__ unit_count, int32_t* __restrict__ track_status) {
+#ifndef AID_PEAKS_MIN_CTAS
+#define AID_PEAKS_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kWarpsPerCta * 32, AID_PEAKS_MIN_CTAS)
+k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units, const aid_peak_run* __restrict__ runs,
+        int n_runs, uint32_t* __restrict__ slots, uint32_t* __restrict__ unit_count, int32_t* __restrict__ track_status) {
     __shared__ WarpSmem s_all[kWarpsPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * kWarpsPerCta + warp;
-    if (unit >= n_units) return;
+    const int run_id = blockIdx.x * kWarpsPerCta + warp;
+    if (run_id >= n_runs) return;
     WarpSmem& sm = s_all[warp];
-    const aid_peak_unit u = units[unit];
-    const int row_end = u.row0 + u.n_rows;
+    const aid_peak_run run = runs[run_id];
+    const aid_peak_unit u = units[run.first_unit];
     Stream st;
     st.T = u.n_frames;
-    st.lo = max(0, u.row0 - kHalfT);
-    st.hi = min(st.T, row_end + kHalfT);
+    st.row0 = u.row0;
+    st.row_end = min(st.T, u.row0 + run.n_blocks * AID_PEAK_BLOCK_FRAMES);
+    st.lo = max(0, st.row0 - kHalfT);
+    st.hi = min(st.T, st.row_end + kHalfT);
     st.base = spec + u.spec_row0 * AID_NBINS;
-    st.out = slots + (int64_t)unit * AID_PEAK_BLOCK_CAP;
+    st.unit = run.first_unit;
+    st.block_end = u.row0 + AID_PEAK_BLOCK_FRAMES;
+    st.out = slots + (int64_t)run.first_unit * AID_PEAK_BLOCK_CAP;
+    st.track = u.track;
+    st.unit_count = unit_count;
+    st.track_status = track_status;
     st.n_peaks = 0;
-    st.fail = false;
     st.jb = 0;
     st.px = -1.0f;
 
-    float4 nxt[4];
-    load_row(nxt, st.base + (int64_t)st.lo * AID_NBINS, lane);
-    for (int r = st.lo; r < st.hi; r++) {
-        const float4 x[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-        if (r + 1 < st.hi) load_row(nxt, st.base + (int64_t)(r + 1) * AID_NBINS, lane);
-        // ---- row pass
-        const float v[16] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w,
-                             x[2].x, x[2].y, x[2].z, x[2].w, x[3].x, x[3].y, x[3].z, x[3].w};
-        float A = v[0];
-#pragma unroll
-        for (int i = 1; i < 16; i++) A = fmaxf(A, v[i]);
-        // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
-        const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
-        const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
-        const float c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
-        uint32_t mask = 0;
-        if (r >= u.row0 && r < row_end && A == c5 && A > AID_PEAK_MIN_S) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) mask |= v[i] == A ? (1u << i) : 0u;
-            if (lane == 0) mask &= ~((1u << AID_PEAK_MIN_BIN) - 1u);
+    // two rows per trip, the next two already in flight
+    float4 na[4], nb[4];
+    load_row(na, st.base + (int64_t)st.lo * AID_NBINS, lane);
+    load_row(nb, st.base + (int64_t)min(st.lo + 1, st.hi - 1) * AID_NBINS, lane);
+    for (int r = st.lo; r < st.hi; r += 2) {
+        const float4 xa[4] = {na[0], na[1], na[2], na[3]};
+        const float4 xb[4] = {nb[0], nb[1], nb[2], nb[3]};
+        if (r + 2 < st.hi) {
+            load_row(na, st.base + (int64_t)(r + 2) * AID_NBINS, lane);
+            load_row(nb, st.base + (int64_t)min(r + 3, st.hi - 1) * AID_NBINS, lane);
         }
-        if (__reduce_add_sync(AID_FULL_MASK, __popc(mask)) > AID_ROW_CAND_CAP) { st.fail = true; mask = 0; }
-        if (st.jb == 2 * kHalfT + 1) {                       // the previous 25-row block is complete: turn its C5
-            float sfx = -1.0f;                               // entries into suffix maxima, start a new block
-#pragma unroll
-            for (int k = 1; k <= 2 * kHalfT + 1; k++) {
-                const int sl = (r - k) & (kRing - 1);
-                sfx = fmaxf(sfx, sm.C5[sl][lane]);
-                sm.C5[sl][lane] = sfx;
-            }
-            st.jb = 0;
-            st.px = -1.0f;
+        row_pass(sm, st, xa, r, lane);
+        if (r - kHalfT >= st.row0) verify_row(sm, st, r - kHalfT, r, lane);
+        if (r + 1 < st.hi) {
+            row_pass(sm, st, xb, r + 1, lane);
+            if (r + 1 - kHalfT >= st.row0) verify_row(sm, st, r + 1 - kHalfT, r + 1, lane);
         }
-        st.jb++;
-        st.px = fmaxf(st.px, c5);
-        const int slot = r & (kRing - 1);
-        sm.A[slot][lane] = A;
-        sm.C5[slot][lane] = c5;
-        sm.M[slot][lane] = (uint16_t)mask;
-        __syncwarp();
-        // ---- column pass for the row whose window has just become complete
-        const int c = r - kHalfT;
-        if (c >= u.row0) verify_row(sm, st, c, r, lane);
-        __syncwarp();
     }
     // rows whose window is cut by the end of the track
-    for (int c = max(u.row0, st.hi - kHalfT); c < row_end; c++) verify_row(sm, st, c, st.hi - 1, lane);
-
-    // ---- order the peaks by (t, f) and publish the unit's list
-    const int n = min(st.n_peaks, AID_PEAK_BLOCK_CAP);
-    int N = 1;
-    while (N < n) N <<= 1;
-    __syncwarp();
-    if (n <= kBuf) {
-        for (int i = n + lane; i < N; i += 32) sm.buf[i] = 0xffffffffu;
-        __syncwarp();
-        warp_sort(sm.buf, N, lane);
-        for (int i = lane; i < n; i += 32) st.out[i] = sm.buf[i];
-    } else {                                               // degenerate input: finish in the slot list itself
-        for (int i = lane; i < kBuf; i += 32) st.out[i] = sm.buf[i];
-        for (int i = n + lane; i < N; i += 32) st.out[i] = 0xffffffffu;
-        __syncwarp();
-        warp_sort(st.out, N, lane);
-    }
-    if (lane == 0) {
-        unit_count[unit] = (uint32_t)n;
-        if (st.n_peaks > AID_PEAK_BLOCK_CAP || st.fail) atomicOr(track_status + u.track, AID_TRACK_PEAK_OVERFLOW);
-    }
+    for (int c = max(st.row0, st.hi - kHalfT); c < st.row_end; c++) verify_row(sm, st, c, st.hi - 1, lane);
+    flush_block(sm, st, lane);
 }
 
 // slots (per unit, fixed capacity) -> dense per-batch peak list in (track, t, f) order
@@ -247,12 +283,12 @@ __global__ void k_peak_compact(const uint32_t* __restrict__ slots, const uint32_
 
 }  // namespace
 
-cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, int n_units,
-                             uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
+cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, const aid_peak_run* d_runs,
+                             int n_runs, uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
                              cudaStream_t st) {
-    if (n_units <= 0) return cudaSuccess;
-    const int grid = (n_units + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_peaks<<<grid, kWarpsPerCta * 32, 0, st>>>(d_spec, d_units, n_units, d_slots, d_unit_count, d_track_status);
+    if (n_runs <= 0) return cudaSuccess;
+    const int grid = (n_runs + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_peaks<<<grid, kWarpsPerCta * 32, 0, st>>>(d_spec, d_units, d_runs, n_runs, d_slots, d_unit_count, d_track_status);
     return cudaGetLastError();
 }
 

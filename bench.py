@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=10000, help="tracks per GPU per step")
     ap.add_argument("--seconds", type=float, default=30.0)
-    ap.add_argument("--sub-batch", type=int, default=512, help="tracks per launch group")
+    ap.add_argument("--sub-batch", type=int, default=2048, help="tracks per launch group")
     ap.add_argument("--cpu-tracks", type=int, default=0)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--no-e2e", action="store_true")

@@ -35,14 +35,8 @@
 #define AID_PEAK_MIN_S    0.001f  /* S must be strictly greater than this             */
 /* a point is a peak iff it passes the two gates above and S equals the maximum of its
  * clipped neighbourhood (all members of an exact tie are peaks).
- * Capacity rules (they only bind on tie-heavy degenerate input, and fail the track):
- *   - a frame may hold at most AID_ROW_CAND_CAP "group candidates": points with S > AID_PEAK_MIN_S and
- *     bin >= AID_PEAK_MIN_BIN that equal the maximum of their aligned AID_GROUP_BINS-bin group [16g, 16g+16)
- *     when that maximum is not below the maxima of the aligned groups g-2, g-1, g+1, g+2 (those that exist);
- *   - every aligned block of AID_PEAK_BLOCK_FRAMES frames [256b, 256b+256) may hold at
- *     most AID_PEAK_BLOCK_CAP peaks. */
-#define AID_GROUP_BINS         16
-#define AID_ROW_CAND_CAP       64
+ * Capacity rule (it only binds on tie-heavy degenerate input, and fails the track): every aligned block of
+ * AID_PEAK_BLOCK_FRAMES frames [256b, 256b+256) may hold at most AID_PEAK_BLOCK_CAP peaks. */
 #define AID_PEAK_BLOCK_FRAMES  256
 #define AID_PEAK_BLOCK_CAP     2048
 #define AID_PEAK_CAP(frames) ((((long long)(frames) + AID_PEAK_BLOCK_FRAMES - 1) / AID_PEAK_BLOCK_FRAMES) * AID_PEAK_BLOCK_CAP)

@@ -134,31 +134,9 @@ static void sliding_max(const float *in, float *out, int64_t n, int64_t stride, 
     }
 }
 
-/* Number of "group candidates" of one frame (capacity rule of aid_params.h). */
-static int row_group_candidates(const float *row) {
-    float gmax[NB / AID_GROUP_BINS];
-    const int ng = NB / AID_GROUP_BINS;
-    for (int g = 0; g < ng; g++) {
-        float m = row[g * AID_GROUP_BINS];
-        for (int i = 1; i < AID_GROUP_BINS; i++) if (row[g * AID_GROUP_BINS + i] > m) m = row[g * AID_GROUP_BINS + i];
-        gmax[g] = m;
-    }
-    int n = 0;
-    for (int g = 0; g < ng; g++) {
-        int top = gmax[g] > AID_PEAK_MIN_S;
-        for (int d = -2; d <= 2 && top; d++) if (g + d >= 0 && g + d < ng && gmax[g + d] > gmax[g]) top = 0;
-        if (!top) continue;
-        for (int i = 0; i < AID_GROUP_BINS; i++) {
-            int f = g * AID_GROUP_BINS + i;
-            if (f >= AID_PEAK_MIN_BIN && row[f] == gmax[g]) n++;
-        }
-    }
-    return n;
-}
-
 /* S[T][512] -> keys[] = (t << 9) | f in (t, f) order. Returns the peak count, or -1 if a
- * capacity rule of aid_params.h is broken (group candidates of a frame > AID_ROW_CAND_CAP, or peaks in an
- * aligned 256-frame block > AID_PEAK_BLOCK_CAP). keys must hold AID_PEAK_CAP(T) entries. */
+ * aligned 256-frame block holds more than AID_PEAK_BLOCK_CAP peaks (capacity rule of aid_params.h).
+ * keys must hold AID_PEAK_CAP(T) entries. */
 int64_t aid_oracle_peaks(const float *S, int64_t T, uint32_t *keys) {
     if (T <= 0) return 0;
     float *m1 = (float *)malloc((size_t)T * NB * sizeof(float));
@@ -169,7 +147,6 @@ int64_t aid_oracle_peaks(const float *S, int64_t T, uint32_t *keys) {
     int64_t n = 0, in_block = 0;
     for (int64_t t = 0; t < T && n >= 0; t++) {
         if (t % AID_PEAK_BLOCK_FRAMES == 0) in_block = 0;
-        if (row_group_candidates(S + t * NB) > AID_ROW_CAND_CAP) { n = -1; break; }
         for (int f = AID_PEAK_MIN_BIN; f < NB; f++) {
             float v = S[t * NB + f];
             if (v > AID_PEAK_MIN_S && v == m2[t * NB + f]) {

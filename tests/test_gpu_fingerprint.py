@@ -194,7 +194,7 @@ def test_sub_batching_does_not_change_results(engine):
     try:
         b = engine.fingerprint(pcm, off)
     finally:
-        engine.set_max_batch_frames(2 * 1024 * 1024)
+        engine.set_max_batch_frames(8 * 1024 * 1024)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
 
