@@ -106,7 +106,7 @@ def run_reference(args, rank):
         return
     from oracle import oracle
     cores = os.cpu_count() or 1
-    n = args.cpu_tracks or max(16, min(256, 2 * cores))
+    n = args.cpu_tracks or max(64, min(2048, 64 * cores))          # about 10 s of work per step for the CPU port
     samples = int(args.seconds * SR)
     pcm = sample_tracks(args, n, samples)
     off = np.arange(n + 1, dtype=np.int64) * samples
@@ -314,7 +314,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle
         cores = os.cpu_count() or 1
-        nc = args.cpu_tracks or max(16, min(256, 2 * cores))
+        nc = args.cpu_tracks or max(64, min(2048, 64 * cores))      # about 10 s of work for the CPU port
         nc = min(nc, n)
         pcm_s = d_pcm[:nc * samples].cpu().numpy()
         off_s = np.arange(nc + 1, dtype=np.int64) * samples
