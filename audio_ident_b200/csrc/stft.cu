@@ -80,7 +80,10 @@ __device__ __forceinline__ float log1p_quarter(float s4) {
     return y * 0.69314718055994531f;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+#ifndef AID_STFT_MIN_CTAS
+#define AID_STFT_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kWarpsPerCta * 32, AID_STFT_MIN_CTAS)
 k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
        const float* __restrict__ pcm, const aid_stft_unit* __restrict__ units, int n_units,
        float* __restrict__ spec) {

@@ -275,18 +275,27 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            off_all = np.arange(n + 1, dtype=np.int64) * samples
-            h_pcm = torch.empty(n * samples, dtype=torch.float32, pin_memory=True)
-            h_pcm.copy_(d_pcm)
+            # pinned host copy of this rank's tracks; never take more than half of the host memory that is free
+            # (all ranks of the box share it)
+            import psutil
+            n_e2e = n
+            budget = psutil.virtual_memory().available * 0.5 / max(world, 1)
+            if n_e2e * samples * 4 > budget:
+                n_e2e = max(1, int(budget // (samples * 4)))
+                log(f"[bench] rank {rank}: e2e leg limited to {n_e2e} tracks per GPU by free host memory")
+            audio_hours_e2e = n_e2e * args.seconds / 3600.0
+            off_all = np.arange(n_e2e + 1, dtype=np.int64) * samples
+            h_pcm = torch.empty(n_e2e * samples, dtype=torch.float32, pin_memory=True)
+            h_pcm.copy_(d_pcm[:n_e2e * samples])
             torch.cuda.synchronize()
             res = eng.fingerprint_dev(d_pcm.data_ptr(), groups[0][1], stream)
             torch.cuda.synchronize()
             per_track = int(eng.to_host(res.d_hash_off, len(groups[0][1]), np.uint32)[-1]) / (len(groups[0][1]) - 1)
-            cap = int(per_track * n * 1.5) + 4096
+            cap = int(per_track * n_e2e * 1.5) + 4096
             h_hash = torch.empty(cap, dtype=torch.int32, pin_memory=True)
             h_t = torch.empty(cap, dtype=torch.int32, pin_memory=True)
-            hoff = np.zeros(n + 1, np.int64)
-            st = np.zeros(n, np.int32)
+            hoff = np.zeros(n_e2e + 1, np.int64)
+            st = np.zeros(n_e2e, np.int32)
             total = 0
             for _ in range(2):
                 total = eng.fingerprint_into(h_pcm, off_all, h_hash.numpy(), h_t.numpy(), hoff, st)
@@ -300,9 +309,9 @@ def main():
             if world > 1:
                 dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
             dt = float(t_e.item()) / args.steps
-            e2e = {"value": world * audio_hours / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * samples * 4),
-                   "d2h_bytes_per_step": int(total * 8 + (n + 1) * 4 + n * 4), "ms_per_step": dt * 1e3,
-                   "hashes_per_step": int(total), "failed_tracks": int((st & 3 != 0).sum())}
+            e2e = {"value": world * audio_hours_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_e2e * samples * 4),
+                   "d2h_bytes_per_step": int(total * 8 + (n_e2e + 1) * 4 + n_e2e * 4), "ms_per_step": dt * 1e3,
+                   "tracks_per_gpu": n_e2e, "hashes_per_step": int(total), "failed_tracks": int((st & 3 != 0).sum())}
             del h_pcm
         except Exception as ex:
             log(f"[bench] e2e leg failed: {ex!r}")
