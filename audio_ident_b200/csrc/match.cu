@@ -76,14 +76,15 @@ struct MatchSmem {
 
 __global__ void __launch_bounds__(kThreads)
 k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, const uint32_t* __restrict__ hash_off,
-        const int32_t* __restrict__ q_status, const aid_seg_desc* __restrict__ segs, int n_seg,
+        const uint32_t* __restrict__ hash_len, const int32_t* __restrict__ q_status,
+        const aid_seg_desc* __restrict__ segs, int n_seg,
         CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n) {
     __shared__ MatchSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = blockIdx.x / n_seg, sg = blockIdx.x % n_seg;
     const aid_seg_desc seg = segs[sg];
     const uint32_t h0 = hash_off[q];
-    const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : hash_off[q + 1] - h0;
+    const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : (hash_len ? hash_len[q] : hash_off[q + 1] - h0);
     const uint32_t* __restrict__ bucket = seg.bucket;
     const uint32_t* __restrict__ postings = seg.postings;
 
@@ -284,32 +285,64 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
 
 }  // namespace
 
-// Runs the matcher for n_q windows whose fingerprints are on the device (dense, hash_off u32[n_q+1]).
-static int match_device(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
-                        const int32_t* d_status, int n_q, aid_match_row* rows, int max_rows, int32_t* n_rows,
-                        cudaStream_t st) {
+// Runs the matcher for n_q windows whose fingerprints are on the device: window q owns
+// hash/t[hash_off[q] .. +len), len = hash_len[q] if given, else hash_off[q+1] - hash_off[q].
+// Rows and counts are written to device memory (d_rows[n_q][max_rows], d_n_rows[n_q]); asynchronous on st.
+static int match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
+                            const uint32_t* d_hash_len, const int32_t* d_status, int n_q, aid_match_row* d_rows,
+                            int max_rows, int32_t* d_n_rows, cudaStream_t st) {
     Index* ix = e->index;
     int rc = aid_index_commit_on(e, st);
     if (rc) return rc;
     const int n_seg = (int)ix->segs.size();
-    if (n_seg == 0 || n_q == 0) { for (int i = 0; i < n_q; i++) n_rows[i] = 0; return AID_OK; }
+    if (n_q == 0) return AID_OK;
+    if (n_seg == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
     const int64_t n_cta = (int64_t)n_q * n_seg;
     if (n_cta >= ((int64_t)1 << 31)) return AID_E_ARG;
     AID_CUDA(e, ix->cand.ensure((size_t)n_cta * AID_MAX_ROWS * sizeof(CandEntry)));
     AID_CUDA(e, ix->cand_n.ensure((size_t)n_cta * 4));
-    AID_CUDA(e, ix->rows.ensure((size_t)n_q * max_rows * sizeof(aid_match_row)));
-    AID_CUDA(e, ix->rows_n.ensure((size_t)n_q * 4));
     { StageTimer tm(e, st, 4);
-    k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
+    k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
                                                   ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>()); }
     { StageTimer tm(e, st, 5);
     k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
-                                     max_rows, ix->rows.as<aid_match_row>(), ix->rows_n.as<int32_t>()); }
+                                     max_rows, d_rows, d_n_rows); }
     AID_CUDA(e, cudaGetLastError());
     e->launches += 2;
+    return AID_OK;
+}
+
+// Same, rows copied to host buffers (synchronous).
+static int match_device(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
+                        const int32_t* d_status, int n_q, aid_match_row* rows, int max_rows, int32_t* n_rows,
+                        cudaStream_t st) {
+    Index* ix = e->index;
+    if (n_q == 0) return AID_OK;
+    AID_CUDA(e, ix->rows.ensure((size_t)n_q * max_rows * sizeof(aid_match_row)));
+    AID_CUDA(e, ix->rows_n.ensure((size_t)n_q * 4));
+    int rc = match_device_out(e, d_hash, d_t, d_hash_off, nullptr, d_status, n_q, ix->rows.as<aid_match_row>(), max_rows,
+                              ix->rows_n.as<int32_t>(), st);
+    if (rc) return rc;
     AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.p, (size_t)n_q * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, st));
     AID_CUDA(e, cudaMemcpyAsync(n_rows, ix->rows_n.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
     AID_CUDA(e, cudaStreamSynchronize(st));
+    return AID_OK;
+}
+
+extern "C" int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t_anchor, const uint32_t* d_hash_off,
+                             const uint32_t* d_hash_len, const int32_t* d_status, int n_queries,
+                             aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream) {
+    if (!e || n_queries < 0 || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
+    if (n_queries > 0 && (!d_hash_off || !d_rows || !d_n_rows)) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    return match_device_out(e, d_hash, d_t_anchor, d_hash_off, d_hash_len, d_status, n_queries, d_rows, max_rows, d_n_rows,
+                            stream ? (cudaStream_t)stream : e->slot[0].st);
+}
+
+extern "C" int aid_copy_device(aid_engine* e, void* d_dst, const void* d_src, int64_t bytes, void* stream) {
+    if (!e || bytes < 0) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    if (bytes > 0) AID_CUDA(e, cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : e->slot[0].st));
     return AID_OK;
 }
 

@@ -280,6 +280,16 @@ class Engine:
                                              nr.ctypes.data_as(C.POINTER(C.c_int32))))
         return rows[:n], nr[:n]
 
+    def match_dev(self, d_hash, d_t, d_hash_off, d_hash_len, d_status, n_queries: int, d_rows, d_n_rows,
+                  max_rows: int = MAX_ROWS, stream=None) -> None:
+        """Device in, device out, asynchronous: see aid_match_dev in include/audio_ident_b200.h."""
+        self._check(self._L.aid_match_dev(self._h, _ptr(d_hash), _ptr(d_t), _ptr(d_hash_off), _ptr(d_hash_len),
+                                          _ptr(d_status), int(n_queries), _ptr(d_rows), int(max_rows), _ptr(d_n_rows),
+                                          _ptr(stream)))
+
+    def copy_device(self, d_dst, d_src, nbytes: int, stream=None) -> None:
+        self._check(self._L.aid_copy_device(self._h, _ptr(d_dst), _ptr(d_src), int(nbytes), _ptr(stream)))
+
     # -- raw device memory (bindings without a CUDA runtime of their own) --------------------------------
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()

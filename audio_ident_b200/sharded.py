@@ -81,6 +81,7 @@ class ShardedIdentifier:
         self.backend, self.rank, self.world, self.group, self.device = backend, rank, world, group, device
         self.to_global: list[int] = []          # local track number -> global track number
         self._to_global_dev = None
+        self._stream = None
 
     # ---- ingest: no collective
     def my_tracks(self, n_global: int, first: int = 0) -> list[int]:
@@ -110,20 +111,12 @@ class ShardedIdentifier:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out.reshape((self.world,) + tuple(t.shape))
 
-    def _merge_local(self, rows: np.ndarray, n: np.ndarray):
-        """this rank's structured rows -> global numbering -> exchange -> merged [n_q, 50, 5], n_rows."""
-        if self.device is None:                                     # CPU path (gloo tests, single process)
-            local = rows_to_array(rows, n, np.asarray(self.to_global, np.int64))
-            if self.world == 1:
-                return merge_rows(local[None])
-            import torch
-            return merge_rows(self._all_gather(torch.from_numpy(local)).numpy())
+    def _merge_device(self, raw, nn):
+        """raw int32 [n_q, max_rows, 5] + counts on the device -> global numbering -> exchange -> merge (all on the GPU)."""
         import torch
         if self._to_global_dev is None:
             self._to_global_dev = torch.tensor(self.to_global if self.to_global else [0], dtype=torch.int64, device=self.device)
-        n_q = rows.shape[0]
-        raw = torch.from_numpy(rows.view(np.int32).reshape(n_q, rows.shape[1], 5)).to(self.device, non_blocking=True)
-        nn = torch.from_numpy(n).to(self.device, non_blocking=True)
+        n_q = raw.shape[0]
         blk = torch.full((n_q, MAX_ROWS, 5), -1, dtype=torch.int64, device=self.device)
         blk[:, :raw.shape[1]] = raw.to(torch.int64)
         blk[:, :, 1] = self._to_global_dev[(blk[:, :, 1] & 0xFFFFFFFF).clamp_(0, len(self._to_global_dev) - 1)]
@@ -133,11 +126,68 @@ class ShardedIdentifier:
             return merge_rows(blk[None])
         return merge_rows(self._all_gather(blk))
 
+    def _query_device(self, d_pcm, sample_off):
+        """Whole identification step without host round trips: split fingerprinting, NCCL all-gather of the hashes
+        (padded to the largest rank), local probe/vote on device buffers, all-gather of the row blocks, merge.
+        One host synchronisation (the per-rank hash totals, needed to size the exchange buffer)."""
+        import torch
+        P, r = self.world, self.rank
+        n = len(sample_off) - 1
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=self.device)
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._stream):
+            st = self._stream.cuda_stream
+            bounds = [q * n // P for q in range(P + 1)]
+            lo, hi = bounds[r], bounds[r + 1]
+            per = max(bounds[q + 1] - bounds[q] for q in range(P))
+            res = self.backend.fingerprint_dev(d_pcm, sample_off[lo:hi + 1], st)
+            i32 = dict(dtype=torch.int32, device=self.device)
+            off = torch.zeros(per + 1, **i32)
+            stat = torch.zeros(per, **i32)
+            self.backend.copy_device(off, res.d_hash_off, 4 * (hi - lo + 1), st)
+            self.backend.copy_device(stat, res.d_status, 4 * (hi - lo), st)
+            lens = off[1:] - off[:-1]
+            lens = torch.where((stat & 3) != 0, torch.zeros_like(lens), lens)
+            lens[hi - lo:] = 0
+            meta = torch.cat([off[hi - lo:hi - lo + 1], off[:-1], lens])          # total, begins[per], lens[per]
+            metas = self._all_gather(meta) if P > 1 else meta[None]
+            totals = metas[:, 0].tolist()                                           # the one host synchronisation
+            cap = max(int(max(totals)), 1)
+            buf = torch.zeros((2, cap), **i32)
+            self.backend.copy_device(buf[0], res.d_hash, 4 * totals[r], st)
+            self.backend.copy_device(buf[1], res.d_t_anchor, 4 * totals[r], st)
+            allb = self._all_gather(buf) if P > 1 else buf[None]                    # [P, 2, cap]
+            begins = torch.cat([metas[q, 1:1 + bounds[q + 1] - bounds[q]] + q * 2 * cap for q in range(P)]).contiguous()
+            lens_all = torch.cat([metas[q, 1 + per:1 + per + bounds[q + 1] - bounds[q]] for q in range(P)]).contiguous()
+            rows = torch.empty((n, MAX_ROWS, 5), **i32)
+            nrows = torch.empty(n, **i32)
+            self.backend.match_dev(allb.data_ptr(), allb.data_ptr() + 4 * cap, begins, lens_all, None, n, rows, nrows,
+                                   MAX_ROWS, st)
+            out = self._merge_device(rows, nrows)
+        torch.cuda.current_stream(self.device).wait_stream(self._stream)
+        return out
+
+    def _merge_local(self, rows: np.ndarray, n: np.ndarray):
+        """this rank's structured rows -> global numbering -> exchange -> merged [n_q, 50, 5], n_rows."""
+        if self.device is None:                                     # CPU path (gloo tests, single process)
+            local = rows_to_array(rows, n, np.asarray(self.to_global, np.int64))
+            if self.world == 1:
+                return merge_rows(local[None])
+            import torch
+            return merge_rows(self._all_gather(torch.from_numpy(local)).numpy())
+        import torch
+        n_q = rows.shape[0]
+        raw = torch.from_numpy(rows.view(np.int32).reshape(n_q, rows.shape[1], 5)).to(self.device, non_blocking=True)
+        return self._merge_device(raw, torch.from_numpy(n).to(self.device, non_blocking=True))
+
     def query(self, pcm, sample_off, device: bool = False, split_fingerprint: bool = True):
         """Every rank passes the same query batch. With several ranks the fingerprinting itself is split (rank r
         fingerprints windows [r*n/P, (r+1)*n/P), hashes are all-gathered) so that no stage is replicated."""
         sample_off = np.ascontiguousarray(sample_off, np.int64)
         n = len(sample_off) - 1
+        if device and self.device is not None and split_fingerprint and n >= self.world and hasattr(self.backend, "match_dev"):
+            return self._query_device(pcm, sample_off)
         if self.world == 1 or not split_fingerprint or n < self.world:
             rows, nr = self.backend.query(pcm, sample_off, device=device)
             return self._merge_local(rows, nr)

@@ -156,11 +156,21 @@ int aid_query_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, 
 int aid_query_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anchor, const int64_t* hash_off,
                      int n_queries, aid_match_row* rows, int max_rows, int32_t* n_rows);
 
+/* device in, device out, asynchronous on `stream`: window q owns d_hash/d_t_anchor[d_hash_off[q] .. +len) with
+ * len = d_hash_len[q] if d_hash_len is given, else d_hash_off[q+1] - d_hash_off[q] (u32 offsets, as produced by
+ * aid_fingerprint_dev); d_status may be NULL; d_rows[n_queries][max_rows], d_n_rows[n_queries] are caller-allocated
+ * device buffers. This is what the multi-GPU path uses between the NCCL exchanges (no host round trip). */
+int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t_anchor, const uint32_t* d_hash_off,
+                  const uint32_t* d_hash_len, const int32_t* d_status, int n_queries,
+                  aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream);
+
 /* ---- helpers for bindings that do not link the CUDA runtime themselves ---------------------- */
 int aid_device_alloc(aid_engine* e, int64_t bytes, void** d_ptr);
 int aid_device_free(aid_engine* e, void* d_ptr);
 int aid_copy_to_device(aid_engine* e, void* d_dst, const void* h_src, int64_t bytes);
 int aid_copy_to_host(aid_engine* e, void* h_dst, const void* d_src, int64_t bytes);
+/* device-to-device, asynchronous on `stream` (e.g. engine-owned results into a torch tensor) */
+int aid_copy_device(aid_engine* e, void* d_dst, const void* d_src, int64_t bytes, void* stream);
 /* fills d_pcm with the deterministic device-side synthetic corpus used by bench.py: track k of the
  * batch is global track number first_track + k; all tracks have samples_per_track samples. */
 int aid_synth_tracks_dev(aid_engine* e, float* d_pcm, int64_t first_track, int n_tracks,

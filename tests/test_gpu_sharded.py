@@ -40,3 +40,27 @@ def test_two_shards_equal_one_index(engine, oracle):
     hits = sum(int(n[3 * q] > 0 and merged[3 * q, 0, 1] in (q, 10, 11) ) for q in range(8))
     assert hits == 8
     engine.index_clear()
+
+
+def test_device_resident_query_path_equals_host_path(engine, oracle):
+    """ShardedIdentifier.query(device=True) (fingerprint_dev -> aid_match_dev -> GPU merge, no host round trip)
+    against the plain host-buffer query on the same index."""
+    torch = pytest.importorskip("torch")
+    tracks = [synth.make_track(800 + k, 8.0) for k in range(6)]
+    engine.index_clear()
+    pcm, off = ragged(tracks)
+    sh = sharded.ShardedIdentifier(engine, 0, 1, device=torch.device("cuda", 0))
+    assert sh.add(pcm, off, list(range(len(tracks)))).all()
+    wins = [tracks[k % 6][4000 * k:4000 * k + 56000] for k in range(9)] + [np.zeros(300, np.float32)]
+    qp, qo = ragged(wins)
+    rows, n = engine.query(qp, qo)
+    ref = sharded.rows_to_array(rows, n, np.arange(len(tracks)))
+    d = torch.from_numpy(qp).cuda()
+    merged, nn = sh.query(d.data_ptr(), qo, device=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(nn.cpu().numpy(), n)
+    m = merged.cpu().numpy()
+    for q in range(len(wins)):
+        assert np.array_equal(m[q, :n[q]], ref[q, :n[q]]), q
+    assert (n[:9] >= 1).all() and n[9] == 0
+    engine.index_clear()
