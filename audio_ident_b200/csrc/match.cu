@@ -71,7 +71,7 @@ struct MatchSmem {
     uint64_t bkey[kBest];
     uint32_t bval[kBest];
     uint32_t wsum[kThreads / 32];
-    uint32_t total, used, overflow, nbest;
+    uint32_t total, used, overflow, nbest, hit;
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -110,15 +110,18 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
         return;
     }
     uint32_t R = (total + kVotesPerRound - 1) / kVotesPerRound;
+    // Few votes (the usual case for one window against one segment): they all fit the exact table, so the sketch
+    // and its second pass over the postings are skipped. If a restart is needed the sketch comes back.
+    bool direct = total <= kTableMaxLoad;
 
     for (;;) {                                        // restarted with a finer partition if the exact table fills
         if (tid == 0) { sm.nbest = 0; sm.overflow = 0; }
         for (uint32_t r = 0; r < R; r++) {
-            for (int i = tid; i < kSketch; i += kThreads) sm.sketch[i] = 0;
+            if (!direct) for (int i = tid; i < kSketch; i += kThreads) sm.sketch[i] = 0;
             for (int i = tid; i < kTable; i += kThreads) { sm.tkey[i] = kEmpty; sm.tcnt[i] = 0; sm.tmin[i] = 0xffffffffu; sm.tmax[i] = 0; }
-            if (tid == 0) sm.used = 0;
+            if (tid == 0) { sm.used = 0; sm.hit = 0; }
             __syncthreads();
-            for (int pass = 0; pass < 2; pass++) {
+            for (int pass = direct ? 1 : 0; pass < 2; pass++) {
                 for (uint32_t c0 = 0; c0 < nh; c0 += kQChunk) {
                     const uint32_t nc = min((uint32_t)kQChunk, nh - c0);
                     // stage the chunk: bucket begin, length prefix, time bias
@@ -163,14 +166,14 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
                         if (R > 1 && (m >> 12) % R != r) continue;
                         const uint32_t idx = m & (kSketch - 1);
                         if (pass == 0) { atomicAdd(&sm.sketch[idx], 1u); continue; }
-                        if (sm.sketch[idx] < AID_MIN_VOTES) continue;
+                        if (!direct && sm.sketch[idx] < AID_MIN_VOTES) continue;
                         const uint32_t tq = AID_QUERY_MAX_FRAMES - sm.qadd[lo];
                         uint32_t slot = (m >> 20) & (kTable - 1);
                         for (int probe = 0; probe < kTable; probe++) {
                             const uint32_t old = atomicCAS(&sm.tkey[slot], kEmpty, key);
                             if (old == kEmpty) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
                             if (old == kEmpty || old == key) {
-                                atomicAdd(&sm.tcnt[slot], 1u);
+                                if (atomicAdd(&sm.tcnt[slot], 1u) + 1 == AID_MIN_VOTES) sm.hit = 1;   // a row is born
                                 atomicMin(&sm.tmin[slot], tq);
                                 atomicMax(&sm.tmax[slot], tq);
                                 break;
@@ -183,6 +186,7 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
                 }
             }
             if (sm.overflow) break;
+            if (!sm.hit) continue;                           // nothing reached AID_MIN_VOTES this round (the usual case)
             // ---- merge this round's exact counts into the running top-kBest
             const uint32_t nb = sm.nbest;
             for (int i = tid; i < kSortN; i += kThreads) {
@@ -208,7 +212,7 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
         __syncthreads();
         if (!sm.overflow) break;
         __syncthreads();
-        R *= 2;
+        if (direct) direct = false; else R *= 2;
     }
 
     const uint32_t n = min(sm.nbest, (uint32_t)AID_MAX_ROWS);
