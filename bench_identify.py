@@ -54,7 +54,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("AID_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout
+        os.environ.pop("NCCL_DEBUG", None)          # NCCL prints its version banner on stdout at any debug level
+        if os.environ.get("AID_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["AID_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
