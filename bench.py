@@ -261,18 +261,29 @@ def main():
     stft_bytes = n * samples * 4 * args.steps + total_frames * 512 * 4
     peaks_bytes = total_frames * 512 * 4
     kern = {}
+    # DRAM bytes per launch from the committed ncu capture (profiles/traffic_r01.json), scaled to this run's average
+    # launch size; None if the capture is missing
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+    except Exception:
+        cap = None
     for name, b in (("stft", stft_bytes), ("peaks", peaks_bytes)):
         t_ms, cnt = stage[name]
         ach = b / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0
+        traffic = None
+        if cap and cnt:
+            c = cap["k_" + name]
+            traffic = (c["dram_bytes_read"] + c["dram_bytes_write"]) * (total_frames / cnt) / cap["frames_per_launch"]
         kern[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                      "traffic": None, "launches": cnt, "avg_launch_ms": t_ms / max(cnt, 1),
-                      "share_of_step": t_ms / ms if ms > 0 else None}
+                      "traffic": traffic, "algorithmic_bytes_per_launch": b / max(cnt, 1), "launches": cnt,
+                      "avg_launch_ms": t_ms / max(cnt, 1), "share_of_step": t_ms / ms if ms > 0 else None}
     for name in ("compact", "hash"):
         t_ms, cnt = stage[name]
         kern[name] = {"avg_group_ms": t_ms / max(cnt, 1), "share_of_step": t_ms / ms if ms > 0 else None}
     roofline = {k: kern["stft"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = "k_stft"
     roofline["peak_source"] = peak_src
+    roofline["traffic_source"] = "profiles/traffic_r01.json (ncu --set full), scaled to this run's launch size"
 
     # ---- end to end through the host-buffer C ABI call
     e2e = None
