@@ -9,7 +9,7 @@
 //   0. stage the query's hashes: bucket begin / length per hash, prefix sum of the lengths -> a flat list of
 //      votes, so every thread handles the same number of postings whatever the bucket sizes are;
 //   1. pass 1 adds every vote key (local_track << 18 | t_ref - t_query + bias: one integer add on the posting)
-//      into a 4096-counter shared-memory sketch with atomics;
+//      into a 2048-counter shared-memory sketch with atomics;
 //   2. pass 2 re-reads the postings (now in L2) and inserts only keys whose sketch counter reached
 //      AID_MIN_VOTES into an exact shared-memory hash table (atomicCAS on the key, atomicAdd on the count,
 //      atomicMin/Max on the query time);
@@ -27,11 +27,11 @@
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kSketch = 4096;
+constexpr int kSketch = 2048;
 constexpr int kTable = 256;
 constexpr int kTableMaxLoad = 192;
 constexpr int kQChunk = 512;
-constexpr int kVotesPerRound = 2048;
+constexpr int kVotesPerRound = 1024;
 constexpr int kBest = 64;                 // >= AID_MAX_ROWS, power of two
 constexpr int kSortN = 512;               // kTable + kBest <= kSortN
 constexpr uint32_t kEmpty = 0xffffffffu;
