@@ -83,15 +83,20 @@ struct Stream {             // per-warp state (the same in every lane except px)
     float px;               // per lane: max of C5 over those rows
 };
 
-// Row pass for one row held in registers: group maximum, 5-group maximum, candidate flag -> rings.
-__device__ __forceinline__ void row_pass(WarpSmem& sm, Stream& st, const float4 (&x)[4], int r, int lane) {
-    float A = fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[0].z, x[0].w));
+// Row pass, register part: group maximum A and 5-group maximum C5 of one row. Pure register/shuffle code, so
+// the two rows of a trip can be interleaved by the scheduler.
+__device__ __forceinline__ void row_reduce(const float4 (&x)[4], float& A, float& c5) {
+    A = fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[0].z, x[0].w));
 #pragma unroll
     for (int q = 1; q < 4; q++) A = fmaxf(A, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
     // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
     const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
     const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
-    const float c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
+    c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
+}
+
+// Row pass, ring part: van Herk block bookkeeping, A / C5 / candidate flag into the rings.
+__device__ __forceinline__ void row_commit(WarpSmem& sm, Stream& st, float A, float c5, int r, int lane) {
     if (st.jb == kBlock) {                                   // the previous 25-row block is complete: turn its C5
         float sfx = -1.0f;                                   // entries into suffix maxima, start a new block
 #pragma unroll
@@ -255,10 +260,13 @@ k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
             load_row(na, st.base + (int64_t)(r + 2) * AID_NBINS, lane);
             load_row(nb, st.base + (int64_t)min(r + 3, st.hi - 1) * AID_NBINS, lane);
         }
-        row_pass(sm, st, xa, r, lane);
+        float A0, c0, A1, c1;
+        row_reduce(xa, A0, c0);
+        row_reduce(xb, A1, c1);
+        row_commit(sm, st, A0, c0, r, lane);
         if (r - kHalfT >= st.row0) verify_row(sm, st, r - kHalfT, r, lane);
         if (r + 1 < st.hi) {
-            row_pass(sm, st, xb, r + 1, lane);
+            row_commit(sm, st, A1, c1, r + 1, lane);
             if (r + 1 - kHalfT >= st.row0) verify_row(sm, st, r + 1 - kHalfT, r + 1, lane);
         }
     }
