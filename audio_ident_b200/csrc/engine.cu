@@ -139,13 +139,13 @@ int aid_build_plan(const int64_t* sample_off, int first, int count, int64_t fram
     plan.first_punit.assign(count + 1, 0);
     const int64_t base = sample_off[first];
     // blocks streamed back to back by one warp of the peak kernel: longer runs re-read fewer halo rows, but the
-    // launch needs several waves of warps (148 SMs x 12 resident warps) to balance
+    // launch needs several waves of warps (148 SMs x 16 resident warps) to balance
     int64_t all_blocks = 0;
     for (int i = 0; i < count; i++) {
         const int64_t T = aid_num_frames(sample_off[first + i + 1] - sample_off[first + i]);
         if (T <= frame_limit) all_blocks += (T + AID_PEAK_BLOCK_FRAMES - 1) / AID_PEAK_BLOCK_FRAMES;
     }
-    const int64_t run_blocks = std::max<int64_t>(1, std::min<int64_t>(AID_PEAK_RUN_BLOCKS, all_blocks / (8 * 148 * 12)));
+    const int64_t run_blocks = std::max<int64_t>(1, std::min<int64_t>(AID_PEAK_RUN_BLOCKS, all_blocks / (8 * 148 * 16)));
     for (int i = 0; i < count; i++) {
         const int64_t begin = sample_off[first + i], end = sample_off[first + i + 1];
         if (end < begin) return AID_E_ARG;

@@ -220,7 +220,7 @@ __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int 
 }
 
 #ifndef AID_PEAKS_MIN_CTAS
-#define AID_PEAKS_MIN_CTAS 3
+#define AID_PEAKS_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(kWarpsPerCta * 32, AID_PEAKS_MIN_CTAS)
 k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units, const aid_peak_run* __restrict__ runs,
