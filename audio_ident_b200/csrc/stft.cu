@@ -80,8 +80,11 @@ __device__ __forceinline__ float log1p_quarter(float s4) {
     return y * 0.69314718055994531f;
 }
 
+#ifndef AID_STFT_WINDOW_IN_SMEM
+#define AID_STFT_WINDOW_IN_SMEM 1
+#endif
 #ifndef AID_STFT_MIN_CTAS
-#define AID_STFT_MIN_CTAS 3
+#define AID_STFT_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(kWarpsPerCta * 32, AID_STFT_MIN_CTAS)
 k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -89,6 +92,10 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
        float* __restrict__ spec) {
     __shared__ float2 s_tw[32 * 32];
     __shared__ float2 s_tile[kWarpsPerCta][kTileFloats];
+#if AID_STFT_WINDOW_IN_SMEM
+    __shared__ float s_win[AID_NFFT];
+    for (int i = threadIdx.x; i < AID_NFFT; i += blockDim.x) s_win[i] = window[i];
+#endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_tw[i] = twiddle[i];
@@ -98,9 +105,11 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
     if (unit_id >= n_units) return;
     const aid_stft_unit u = units[unit_id];
 
+#if !AID_STFT_WINDOW_IN_SMEM
     float w[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) w[j] = __ldg(window + lane + 32 * j);
+#endif
 
     // lane's samples: xp[32*m], m = 0.. ; rem = samples left from xp (32-bit: a track has < 2^31 samples)
     const int64_t first = (int64_t)u.frame0 * AID_HOP + lane;
@@ -124,7 +133,14 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
 
         float re[32], im[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) { re[bitrev5(j)] = w[j] * ring[j]; im[bitrev5(j)] = w[j] * ring[j + 4]; }
+        for (int j = 0; j < 32; j++) {
+#if AID_STFT_WINDOW_IN_SMEM
+            const float wj = s_win[lane + 32 * j];
+#else
+            const float wj = w[j];
+#endif
+            re[bitrev5(j)] = wj * ring[j]; im[bitrev5(j)] = wj * ring[j + 4];
+        }
 
         fft32(re, im);                                   // over n2: Y[k1] in element k1
 
