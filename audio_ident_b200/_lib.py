@@ -43,6 +43,7 @@ def load() -> C.CDLL:
     L = C.CDLL(LIB_PATH)
     vp, i64p, i32p, u32p, u8p, f32p = (C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_float))
+    f64p = C.POINTER(C.c_double)
     sig = {
         "aid_abi_version": (C.c_int, []),
         "aid_strerror": (C.c_char_p, [C.c_int]),
@@ -82,6 +83,14 @@ def load() -> C.CDLL:
         "aid_copy_to_device": (C.c_int, [vp, vp, vp, C.c_int64]),
         "aid_copy_to_host": (C.c_int, [vp, vp, vp, C.c_int64]),
         "aid_synth_tracks_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int64, C.c_uint64, vp]),
+        "aid_dedup_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "aid_dedup_destroy": (None, [vp]),
+        "aid_dedup_last_error": (C.c_char_p, [vp]),
+        "aid_dedup_size": (C.c_int64, [vp]),
+        "aid_dedup_launch_count": (C.c_int64, [vp]),
+        "aid_dedup_add": (C.c_int, [vp, vp, i64p, f64p, C.c_int, i64p]),
+        "aid_dedup_scan": (C.c_int, [vp, vp, i64p, f64p, f64p, C.c_int, i64p, f64p]),
+        "aid_dedup_last_scan_ms": (C.c_double, [vp]),
     }
     missing = []
     for name, (res, args) in sig.items():
@@ -108,5 +117,6 @@ EXPORTED = [  # every symbol include/audio_ident_b200.h declares (tests/test_abi
     "aid_index_add_hashes", "aid_index_delete", "aid_index_commit", "aid_index_clear", "aid_index_stats",
     "aid_index_track_name", "aid_index_save", "aid_index_load", "aid_query_host", "aid_query_dev",
     "aid_query_hashes", "aid_match_dev", "aid_copy_device", "aid_device_alloc", "aid_device_free", "aid_copy_to_device", "aid_copy_to_host",
-    "aid_synth_tracks_dev",
+    "aid_synth_tracks_dev", "aid_dedup_create", "aid_dedup_destroy", "aid_dedup_last_error", "aid_dedup_size",
+    "aid_dedup_launch_count", "aid_dedup_add", "aid_dedup_scan", "aid_dedup_last_scan_ms",
 ]

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include "../../include/aid_params.h"
 #include "../../include/audio_ident_b200.h"
 
@@ -32,14 +33,38 @@ struct aid_peak_run {      // one warp of the peak kernel: `n_blocks` consecutiv
 };
 
 #define AID_PEAK_RUN_BLOCKS    4       // blocks streamed back to back by one warp (halo re-read: 24 rows per run)
+#ifndef AID_STFT_UNIT_FRAMES
 #define AID_STFT_UNIT_FRAMES   64      // frames per warp-unit (even)
+#endif
 #define AID_PEAK_BLOCK_FRAMES  256     // must equal the spec's aligned block (aid_params.h)
 
 // ---- kernel launchers (defined in the .cu files, called by engine.cu) --------------
 struct aid_tables {              // device-resident constant tables, built once per engine
-    const float*  window;        // [1024] float32 Hamming
-    const float2* twiddle;       // [32][32] W_1024^(k1*n1), k1-major
+    const float* window;         // [1024] float32 Hamming
+    const float* twist;          // [32 lanes k1][32] twiddles of the second STFT transform, see aid_fill_stft_tables
 };
+
+// Host-side definition of the two tables (double precision, rounded to float once).
+//  window[n] : symmetric Hamming, the formula of oracle/aid_oracle.c tables_init.
+//  twist[k1][2*i], [2*i+1] = (c, s) of the twiddle w = c - i s = g^m * W_(2h)^k with g = W_1024^k1, for
+//    i = 0: stage 0 (m 16, h 1, k 0)      i = 1: stage 1 (m 8, h 2, k 0)      i = 2..3: stage 2 (m 4, h 4, k 0..1)
+//    i = 4..7: stage 3 (m 2, h 8, k 0..3)  i = 8..15: stage 4 (m 1, h 16, k 0..7)
+inline void aid_fill_stft_tables(float* window, float* twist) {
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < AID_NFFT; i++)
+        window[i] = (float)(AID_WIN_A0 - AID_WIN_A1 * cos(two_pi * (double)i / (double)(AID_NFFT - 1)));
+    for (int k1 = 0; k1 < 32; k1++) {
+        int i = 0;
+        for (int stage = 0; stage < 5; stage++) {
+            const int half = 1 << stage, m = 16 >> stage, nk = half >= 2 ? half / 2 : 1;
+            for (int k = 0; k < nk; k++, i++) {
+                const double a = two_pi * ((double)(k1 * m) / (double)AID_NFFT + (double)k / (double)(2 * half));
+                twist[k1 * 32 + 2 * i] = (float)cos(a);
+                twist[k1 * 32 + 2 * i + 1] = (float)sin(a);
+            }
+        }
+    }
+}
 
 cudaError_t aid_launch_stft(const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
                             int n_units, float* d_spec, cudaStream_t st);

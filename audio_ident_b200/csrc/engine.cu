@@ -77,23 +77,15 @@ extern "C" int aid_engine_create(int device, aid_engine** out) {
         if ((ce = cudaStreamCreateWithFlags(&e->slot[i].st, cudaStreamNonBlocking)) != cudaSuccess) return fail(ce, "cudaStreamCreate");
         if ((ce = cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
     }
-    // constant tables: the float32 Hamming window (same formula as oracle/aid_oracle.c tables_init) and
-    // the 32x32 inter-stage twiddles W_1024^(k1*n1), both rounded from double once.
-    std::vector<float> win(AID_NFFT);
-    for (int i = 0; i < AID_NFFT; i++)
-        win[i] = (float)(AID_WIN_A0 - AID_WIN_A1 * cos(2.0 * M_PI * (double)i / (double)(AID_NFFT - 1)));
-    std::vector<float2> tw(32 * 32);
-    for (int k1 = 0; k1 < 32; k1++)
-        for (int n1 = 0; n1 < 32; n1++) {
-            const double a = -2.0 * M_PI * (double)(k1 * n1) / (double)AID_NFFT;
-            tw[k1 * 32 + n1] = make_float2((float)cos(a), (float)sin(a));
-        }
+    // constant tables (definition: aid_fill_stft_tables in common.cuh)
+    std::vector<float> win(AID_NFFT), tw(32 * 32);
+    aid_fill_stft_tables(win.data(), tw.data());
     if ((ce = e->d_window.ensure(win.size() * sizeof(float))) != cudaSuccess) return fail(ce, "cudaMalloc(window)");
-    if ((ce = e->d_twiddle.ensure(tw.size() * sizeof(float2))) != cudaSuccess) return fail(ce, "cudaMalloc(twiddle)");
+    if ((ce = e->d_twiddle.ensure(tw.size() * sizeof(float))) != cudaSuccess) return fail(ce, "cudaMalloc(twist)");
     if ((ce = cudaMemcpy(e->d_window.p, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(ce, "cudaMemcpy(window)");
-    if ((ce = cudaMemcpy(e->d_twiddle.p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(ce, "cudaMemcpy(twiddle)");
+    if ((ce = cudaMemcpy(e->d_twiddle.p, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(ce, "cudaMemcpy(twist)");
     e->tables.window = e->d_window.as<float>();
-    e->tables.twiddle = e->d_twiddle.as<float2>();
+    e->tables.twist = e->d_twiddle.as<float>();
     e->index = aid_index_new();
     *out = e;
     return AID_OK;

@@ -7,21 +7,27 @@
 // Design (see DESIGN.md "STFT kernel"):
 //  * One warp owns a run of consecutive frames of one track. Two frames a, b = a+1 are packed into one
 //    1024-point COMPLEX transform z = a + i*b, factored 32 x 32: lane n1 holds z[n1 + 32*n2] for
-//    n2 = 0..31 in registers, does a 32-point FFT over n2, multiplies by W_1024^(n1*k1), the warp
-//    transposes through its private shared-memory tile, lane k1 does the second 32-point FFT over n1
-//    and ends up holding Z[k1 + 32*k2]. Z[N-k] lives in lane (32-k1)&31, so the two real spectra are
-//    separated with one shuffle per value.
+//    n2 = 0..31 in registers, does a 32-point FFT over n2 (its first stage fused with the window
+//    multiply), the warp transposes through its private shared-memory tile, lane k1 does the second
+//    32-point transform over n1 with the twiddles W_1024^(n1*k1) folded into its butterflies and ends up
+//    holding Z[k1 + 32*k2]. Z[N-k] lives in lane (32-k1)&31, so the two real spectra are separated with
+//    one shuffle per value.
 //  * Because the hop is 128 = 4*32 samples, lane n1 needs x[32*m + n1] for a window of m that slides by 4
 //    per frame: PCM goes global -> registers with fully coalesced 128 B warp loads and every sample is
 //    read from HBM once per unit (8x frame overlap is served from the register ring, never re-read).
 //  * Rows of the spectrogram (512 floats = 2 KB) are written with 128 B coalesced warp stores.
-// The kernel is FP32-issue-bound, not HBM-bound (about 1.3 k FP32 instructions per lane per frame pair).
+// The kernel is FP32-issue-bound, not HBM-bound (about 1.1 k FP32 instructions per lane per frame pair);
+// packed FFMA2/FADD2 were measured to issue at half rate on sm_100a (tools/microbench/fp32_issue.cu), so the
+// butterflies stay scalar.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kTileStride = 33;                        // 32 x 33 floats: conflict-free transpose
+#ifndef AID_STFT_WARPS
+#define AID_STFT_WARPS 4
+#endif
+constexpr int kWarpsPerCta = AID_STFT_WARPS;
+constexpr int kTileStride = 34;                        // float2 per tile row: 16 B aligned rows, conflict-free STS.64 / LDS.128
 constexpr int kTileFloats = 32 * kTileStride;
 
 // W_32^k = cos(2 pi k/32) - i sin(2 pi k/32), k = 0..15
@@ -69,8 +75,65 @@ __device__ __forceinline__ void stage(float (&re)[32], float (&im)[32]) {
     }
 }
 
-__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
-    stage<0, 0>(re, im); stage<1, 0>(re, im); stage<2, 0>(re, im); stage<3, 0>(re, im); stage<4, 0>(re, im);
+// Stages 1..4 of the DIT transform (stage 0 is fused with the window multiply, see k_stft).
+__device__ __forceinline__ void fft32_after_stage0(float (&re)[32], float (&im)[32]) {
+    stage<1, 0>(re, im); stage<2, 0>(re, im); stage<3, 0>(re, im); stage<4, 0>(re, im);
+}
+
+// ---- second transform: the inter-stage twiddle W_1024^(n1*k1) is folded into the butterflies ----
+// Lane k1 needs Z[k2] = sum_n1 y[n1] g^n1 W_32^(n1*k2) with g = W_1024^k1. Splitting n1 into even and odd
+// gives the usual DIT recursion with the twist squared at every level, so stage S (half = 2^S) uses the
+// twiddles g^(16>>S) * W_(2*half)^k, k < half: lane-dependent values from a table (AID_TWIST_*), 16 complex
+// per lane because W^(k + half/2) = -i W^k reuses the same pair with the roles of c and s exchanged.
+// All 80 butterflies are general (6 FMA), which is still fewer instructions than 31 complex multiplies
+// followed by a transform with constant twiddles, and the table costs 8 LDS.128 instead of 31 LDS.64.
+template <int A, int B, bool ROT>
+__device__ __forceinline__ void twisted_butterfly(float (&re)[32], float (&im)[32], float c, float s) {
+    const float ar = re[A], ai = im[A], br = re[B], bi = im[B];
+    float xr, xi;
+    if constexpr (!ROT) {                                   // w = c - i s
+        xr = fmaf(bi, s, fmaf(br, c, ar));
+        xi = fmaf(-br, s, fmaf(bi, c, ai));
+    } else {                                                // w = -i (c - i s) = -s - i c
+        xr = fmaf(bi, c, fmaf(-br, s, ar));
+        xi = fmaf(-br, c, fmaf(-bi, s, ai));
+    }
+    re[A] = xr; im[A] = xi;
+    re[B] = fmaf(2.0f, ar, -xr); im[B] = fmaf(2.0f, ai, -xi);
+}
+
+// butterflies k' and k' + half/2 of every group of stage S, for the two twiddles held in one float4
+template <int S, int KP, int G>
+__device__ __forceinline__ void twisted_groups(float (&re)[32], float (&im)[32], float c, float s) {
+    constexpr int half = 1 << S;
+    if constexpr (G < 16 / half) {
+        constexpr int a0 = G * 2 * half + KP;
+        twisted_butterfly<a0, a0 + half, false>(re, im, c, s);
+        if constexpr (half >= 2) twisted_butterfly<a0 + half / 2, a0 + half / 2 + half, true>(re, im, c, s);
+        twisted_groups<S, KP, G + 1>(re, im, c, s);
+    }
+}
+
+__device__ __forceinline__ void fft32_twisted(float (&re)[32], float (&im)[32], const float4* tw) {
+    const float4 t01 = tw[0];                               // stage 0: g^16 ; stage 1: g^8
+    twisted_groups<0, 0, 0>(re, im, t01.x, t01.y);
+    twisted_groups<1, 0, 0>(re, im, t01.z, t01.w);
+    const float4 t2 = tw[1];                                // stage 2: g^4 W_8^{0,1}
+    twisted_groups<2, 0, 0>(re, im, t2.x, t2.y);
+    twisted_groups<2, 1, 0>(re, im, t2.z, t2.w);
+    const float4 t3a = tw[2], t3b = tw[3];                  // stage 3: g^2 W_16^{0..3}
+    twisted_groups<3, 0, 0>(re, im, t3a.x, t3a.y);
+    twisted_groups<3, 1, 0>(re, im, t3a.z, t3a.w);
+    twisted_groups<3, 2, 0>(re, im, t3b.x, t3b.y);
+    twisted_groups<3, 3, 0>(re, im, t3b.z, t3b.w);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {                           // stage 4: g W_32^{0..7}
+        const float4 t = tw[4 + q];
+        if (q == 0) { twisted_groups<4, 0, 0>(re, im, t.x, t.y); twisted_groups<4, 1, 0>(re, im, t.z, t.w); }
+        if (q == 1) { twisted_groups<4, 2, 0>(re, im, t.x, t.y); twisted_groups<4, 3, 0>(re, im, t.z, t.w); }
+        if (q == 2) { twisted_groups<4, 4, 0>(re, im, t.x, t.y); twisted_groups<4, 5, 0>(re, im, t.z, t.w); }
+        if (q == 3) { twisted_groups<4, 6, 0>(re, im, t.x, t.y); twisted_groups<4, 7, 0>(re, im, t.z, t.w); }
+    }
 }
 
 // log(1 + s4/4) for s4 >= 0: one FFMA, one MUFU.LG2 (the argument is >= 1, so no denormal handling), one FMUL
@@ -80,36 +143,33 @@ __device__ __forceinline__ float log1p_quarter(float s4) {
     return y * 0.69314718055994531f;
 }
 
-#ifndef AID_STFT_WINDOW_IN_SMEM
-#define AID_STFT_WINDOW_IN_SMEM 1
-#endif
 #ifndef AID_STFT_MIN_CTAS
-#define AID_STFT_MIN_CTAS 4
+#define AID_STFT_MIN_CTAS 3
 #endif
+constexpr int kTabStride = 36;                         // floats per lane row of the two lane-major tables (16 B aligned, conflict-free LDS.128)
+
+// 3 CTAs x 4 warps per SM: 142 registers, no spills. Measured alternatives (tools/microbench/stft_bench.cu, 2048 x 30 s
+// tracks): 4 CTAs (128 registers, 20 B of spills) 50.9 %, 7 x 2 warps at 144 registers 52.8 %, this shape 52.8 % of the
+// HBM roofline; unrolling the pair loop to rename the sample ring away costs more in instruction fetch than the 40 MOVs
+// it removes (44 % / 36 % at x2 / x3).
 __global__ void __launch_bounds__(kWarpsPerCta * 32, AID_STFT_MIN_CTAS)
-k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
+k_stft(const float* __restrict__ window, const float* __restrict__ twist,
        const float* __restrict__ pcm, const aid_stft_unit* __restrict__ units, int n_units,
        float* __restrict__ spec) {
-    __shared__ float2 s_tw[32 * 32];
-    __shared__ float2 s_tile[kWarpsPerCta][kTileFloats];
-#if AID_STFT_WINDOW_IN_SMEM
-    __shared__ float s_win[AID_NFFT];
-    for (int i = threadIdx.x; i < AID_NFFT; i += blockDim.x) s_win[i] = window[i];
-#endif
+    __shared__ __align__(16) float s_win[32 * kTabStride];       // [lane][j]  = window[lane + 32 j]
+    __shared__ __align__(16) float s_twist[32 * kTabStride];     // [lane][..] = AID_TWIST layout (engine.cu)
+    __shared__ __align__(16) float2 s_tile[kWarpsPerCta][kTileFloats];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_tw[i] = twiddle[i];
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+        s_win[(i & 31) * kTabStride + (i >> 5)] = window[i];
+        s_twist[(i >> 5) * kTabStride + (i & 31)] = twist[i];
+    }
     __syncthreads();
 
     const int unit_id = blockIdx.x * kWarpsPerCta + warp;
     if (unit_id >= n_units) return;
     const aid_stft_unit u = units[unit_id];
-
-#if !AID_STFT_WINDOW_IN_SMEM
-    float w[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) w[j] = __ldg(window + lane + 32 * j);
-#endif
 
     // lane's samples: xp[32*m], m = 0.. ; rem = samples left from xp (32-bit: a track has < 2^31 samples)
     const int64_t first = (int64_t)u.frame0 * AID_HOP + lane;
@@ -121,6 +181,9 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
     for (int j = 0; j < 36; j++) ring[j] = 32 * j < rem ? __ldg(xp + 32 * j) : 0.0f;
 
     float2* tile = s_tile[warp];
+    const float4* tile_row = reinterpret_cast<const float4*>(tile + lane * kTileStride);
+    const float4* win4 = reinterpret_cast<const float4*>(s_win + lane * kTabStride);
+    const float4* twist4 = reinterpret_cast<const float4*>(s_twist + lane * kTabStride);
     const int partner = (32 - lane) & 31;
     float* row_a = spec + u.spec_row * AID_NBINS + lane;
 
@@ -131,35 +194,35 @@ k_stft(const float* __restrict__ window, const float2* __restrict__ twiddle,
         xp += 2 * AID_HOP;
         rem -= 2 * AID_HOP;
 
+        // window multiply fused with DIT stage 0 (pairs samples j and j + 16): frame a in re, frame b = a + 1 in im
         float re[32], im[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-#if AID_STFT_WINDOW_IN_SMEM
-            const float wj = s_win[lane + 32 * j];
-#else
-            const float wj = w[j];
-#endif
-            re[bitrev5(j)] = wj * ring[j]; im[bitrev5(j)] = wj * ring[j + 4];
-        }
-
-        fft32(re, im);                                   // over n2: Y[k1] in element k1
-
-        // twiddle W_1024^(lane * k1), then scatter Y[k1] to tile[k1][lane]
-        tile[lane] = make_float2(re[0], im[0]);
+        for (int q = 0; q < 4; q++) {
+            const float4 wa4 = win4[q], wb4 = win4[4 + q];
+            const float wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
 #pragma unroll
-        for (int k1 = 1; k1 < 32; k1++) {
-            const float2 t = s_tw[k1 * 32 + lane];
-            tile[k1 * kTileStride + lane] = make_float2(fmaf(re[k1], t.x, -im[k1] * t.y), fmaf(re[k1], t.y, im[k1] * t.x));
+            for (int r = 0; r < 4; r++) {
+                const int ja = 4 * q + r, jb = ja + 16, e = bitrev5(ja);
+                const float tr = wb[r] * ring[jb], ti = wb[r] * ring[jb + 4];
+                re[e] = fmaf(wa[r], ring[ja], tr);     re[e + 1] = fmaf(wa[r], ring[ja], -tr);
+                im[e] = fmaf(wa[r], ring[ja + 4], ti); im[e + 1] = fmaf(wa[r], ring[ja + 4], -ti);
+            }
         }
+        fft32_after_stage0(re, im);                      // over n2: Y[k1] in element k1
+
+        // transpose: lane n1 scatters Y[k1] to tile[k1][n1]; lane k1 gathers its row two values at a time
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++) tile[k1 * kTileStride + lane] = make_float2(re[k1], im[k1]);
         __syncwarp();
 #pragma unroll
-        for (int n1 = 0; n1 < 32; n1++) {                // lane = k1 gathers all n1
-            const float2 z = tile[lane * kTileStride + n1];
-            re[bitrev5(n1)] = z.x; im[bitrev5(n1)] = z.y;
+        for (int q = 0; q < 16; q++) {
+            const float4 z = tile_row[q];
+            re[bitrev5(2 * q)] = z.x;     im[bitrev5(2 * q)] = z.y;
+            re[bitrev5(2 * q + 1)] = z.z; im[bitrev5(2 * q + 1)] = z.w;
         }
         __syncwarp();
 
-        fft32(re, im);                                   // over n1: Z[lane + 32*k2] in element k2
+        fft32_twisted(re, im, twist4);                   // over n1: Z[lane + 32*k2] in element k2
 
         const bool has_b = p + 1 < u.n_frames;
 #pragma unroll
@@ -190,6 +253,6 @@ cudaError_t aid_launch_stft(const aid_tables& tb, const float* d_pcm, const aid_
                             int n_units, float* d_spec, cudaStream_t st) {
     if (n_units <= 0) return cudaSuccess;
     const int grid = (n_units + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_stft<<<grid, kWarpsPerCta * 32, 0, st>>>(tb.window, tb.twiddle, d_pcm, d_units, n_units, d_spec);
+    k_stft<<<grid, kWarpsPerCta * 32, 0, st>>>(tb.window, tb.twist, d_pcm, d_units, n_units, d_spec);
     return cudaGetLastError();
 }

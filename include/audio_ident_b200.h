@@ -164,6 +164,31 @@ int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t_anc
                   const uint32_t* d_hash_len, const int32_t* d_status, int n_queries,
                   aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream);
 
+/* ---- content-duplicate scan ----------------------------------------------
+ * Replaces the per-row Python loop of audio-ident-service/app/audio/dedup.py:170-222 (check_content_duplicate)
+ * and its inner _fingerprint_similarity (:127-167). A store keeps the raw Chromaprint fingerprints of every
+ * ingested track resident in HBM: row r = words[off[r] .. off[r+1]) (each word one 32-bit sub-fingerprint,
+ * the integers of `fpcalc -raw` taken modulo 2^32 as dedup.py:158 does) with its chromaprint_duration.
+ * A scan answers, per query, the reference's loop: among rows with q_lo <= duration <= q_hi (the caller
+ * passes duration*0.9 and duration*1.1 computed in double, dedup.py:189-190) the row with the greatest
+ * similarity, the first such row on ties; best_row = -1 and best_sim = 0.0 if no row has similarity > 0.
+ * best_sim is the IEEE double the reference's Python computes, bit for bit. The threshold test
+ * (dedup.py:214) stays with the caller. Calls on one store must be serialised by the caller. */
+typedef struct aid_dedup aid_dedup;
+int         aid_dedup_create(int device, aid_dedup** out);
+void        aid_dedup_destroy(aid_dedup* d);
+const char* aid_dedup_last_error(const aid_dedup* d);
+int64_t     aid_dedup_size(const aid_dedup* d);
+int64_t     aid_dedup_launch_count(const aid_dedup* d);
+/* appends n rows; word_off[0] = 0; *first_row receives the row number of the first one */
+int aid_dedup_add(aid_dedup* d, const uint32_t* words, const int64_t* word_off /* [n+1] */,
+                  const double* duration /* [n] */, int n, int64_t* first_row);
+int aid_dedup_scan(aid_dedup* d, const uint32_t* q_words, const int64_t* q_off /* [nq+1] */,
+                   const double* q_lo, const double* q_hi, int nq,
+                   int64_t* best_row /* [nq] */, double* best_sim /* [nq] */);
+/* device time of the last scan's kernels (CUDA events on the store's stream), milliseconds */
+double      aid_dedup_last_scan_ms(const aid_dedup* d);
+
 /* ---- helpers for bindings that do not link the CUDA runtime themselves ---------------------- */
 int aid_device_alloc(aid_engine* e, int64_t bytes, void** d_ptr);
 int aid_device_free(aid_engine* e, void* d_ptr);

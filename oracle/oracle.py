@@ -18,11 +18,11 @@ ROW_DTYPE = np.dtype([("count", "<i4"), ("track", "<u4"), ("offset", "<i4"),
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "aid_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "aid_params.h")
+    srcs = [os.path.join(_HERE, "aid_oracle.c"), os.path.join(_HERE, "dedup_oracle.c"),
+            os.path.join(_HERE, "..", "include", "aid_params.h")]
     stale = (not os.path.exists(_SO)) or force
-    if not stale and os.path.exists(src):
-        stale = os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if not stale and all(os.path.exists(s) for s in srcs):
+        stale = os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs)
     if stale:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
@@ -48,6 +48,10 @@ def lib():
         L.aid_oracle_match.argtypes = [u32p, u32p, u64p, u8p, u32p, u32p, C.c_int64, C.c_void_p, C.c_int]
         L.aid_oracle_match.restype = C.c_int
         L.aid_oracle_params.argtypes = [C.POINTER(C.c_int32)]
+        f64p = C.POINTER(C.c_double)
+        L.aid_oracle_fp_similarity.argtypes = [u32p, C.c_int64, u32p, C.c_int64]
+        L.aid_oracle_fp_similarity.restype = C.c_double
+        L.aid_oracle_dedup_scan.argtypes = [u32p, i64p, f64p, C.c_int64, u32p, i64p, f64p, f64p, C.c_int, i64p, f64p, C.c_int]
         _lib = L
     return _lib
 
@@ -152,3 +156,23 @@ class Index:
                                    tomb, _p(q_hash, C.c_uint32), _p(q_t, C.c_uint32), len(q_hash),
                                    rows.ctypes.data, max_rows)
         return rows[:n].copy()
+
+
+# ---------------------------------------------------------------- content-duplicate scan (dedup_oracle.c)
+def fp_similarity(a: np.ndarray, b: np.ndarray) -> float:
+    a = np.ascontiguousarray(a, dtype=np.uint32); b = np.ascontiguousarray(b, dtype=np.uint32)
+    return float(lib().aid_oracle_fp_similarity(_p(a, C.c_uint32), a.size, _p(b, C.c_uint32), b.size))
+
+
+def dedup_scan(words, off, dur, q_words, q_off, q_lo, q_hi, n_threads: int = 0):
+    """Best row (-1 if none) and similarity per query; arguments as aid_dedup_add / aid_dedup_scan."""
+    words = np.ascontiguousarray(words, dtype=np.uint32); off = np.ascontiguousarray(off, dtype=np.int64)
+    dur = np.ascontiguousarray(dur, dtype=np.float64)
+    q_words = np.ascontiguousarray(q_words, dtype=np.uint32); q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+    q_lo = np.ascontiguousarray(q_lo, dtype=np.float64); q_hi = np.ascontiguousarray(q_hi, dtype=np.float64)
+    nq = q_lo.size
+    best_row = np.full(nq, -1, dtype=np.int64); best_sim = np.zeros(nq, dtype=np.float64)
+    lib().aid_oracle_dedup_scan(_p(words, C.c_uint32), _p(off, C.c_int64), _p(dur, C.c_double), dur.size,
+                                _p(q_words, C.c_uint32), _p(q_off, C.c_int64), _p(q_lo, C.c_double),
+                                _p(q_hi, C.c_double), nq, _p(best_row, C.c_int64), _p(best_sim, C.c_double), n_threads)
+    return best_row, best_sim

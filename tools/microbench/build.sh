@@ -1,0 +1,12 @@
+#!/bin/bash
+# Builds the standalone micro-benchmarks of this directory into bin/ (sm_100a).
+#   fp32_issue        issue rate of scalar vs packed FP32 instructions
+#   stft_bench        k_stft alone: timing + double-precision spot check (STFT_FLAGS="-DAID_STFT_WARPS=2 ..." builds a variant)
+set -e
+cd "$(dirname "$0")"
+mkdir -p bin
+F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"
+S=../../audio_ident_b200/csrc/stft.cu
+nvcc $F -o bin/fp32_issue fp32_issue.cu
+nvcc $F $STFT_FLAGS -o bin/stft_bench stft_bench.cu $S
+echo built
