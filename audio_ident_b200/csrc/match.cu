@@ -62,6 +62,25 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* key, uint32_t* val, int t
         }
 }
 
+// same network on the first n slots only (n a power of two <= the array size; slots >= n are not touched)
+template <int T>
+__device__ __forceinline__ void bitonic_sort_n(uint64_t* key, uint32_t* val, int n, int tid) {
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += T) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint64_t a = key[i], b = key[p];
+                    if ((a > b) == ((i & k) == 0)) {
+                        key[i] = b; key[p] = a;
+                        const uint32_t t = val[i]; val[i] = val[p]; val[p] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
 struct MatchSmem {
     uint32_t sketch[kSketch];
     uint32_t tkey[kTable], tcnt[kTable], tmin[kTable], tmax[kTable];
@@ -264,10 +283,13 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
             __syncthreads();
             sg++;
         }
-        bitonic_sort<kRankN, kThreads>(skey, sval, tid);
+        // most windows have a handful of candidate rows in one segment: sort only as many slots as are filled
+        int width = 32;
+        while (width < (int)s_fill) width <<= 1;
+        bitonic_sort_n<kThreads>(skey, sval, width, tid);
         if (tid == 0) {
             uint32_t n = 0;
-            while (n < kBest && skey[n] != kPad) n++;
+            while (n < kBest && n < (uint32_t)width && skey[n] != kPad) n++;
             s_best = n;
         }
         __syncthreads();

@@ -136,10 +136,11 @@ __device__ __forceinline__ void fft32_twisted(float (&re)[32], float (&im)[32], 
     }
 }
 
-// log(1 + s4/4) for s4 >= 0: one FFMA, one MUFU.LG2 (the argument is >= 1, so no denormal handling), one FMUL
-__device__ __forceinline__ float log1p_quarter(float s4) {
+// log(1 + re^2 + im^2): two FFMA (the "+1" rides on the first), one MUFU.LG2 (the argument is >= 1, so no denormal
+// handling), one FMUL
+__device__ __forceinline__ float log1p_power(float re, float im) {
     float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(0.25f, s4, 1.0f)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(re, re, fmaf(im, im, 1.0f))));
     return y * 0.69314718055994531f;
 }
 
@@ -151,7 +152,8 @@ constexpr int kTabStride = 36;                         // floats per lane row of
 // 3 CTAs x 4 warps per SM: 142 registers, no spills. Measured alternatives (tools/microbench/stft_bench.cu, 2048 x 30 s
 // tracks): 4 CTAs (128 registers, 20 B of spills) 50.9 %, 7 x 2 warps at 144 registers 52.8 %, this shape 52.8 % of the
 // HBM roofline; unrolling the pair loop to rename the sample ring away costs more in instruction fetch than the 40 MOVs
-// it removes (44 % / 36 % at x2 / x3).
+// it removes (44 % / 36 % at x2 / x3); twiddles of the first transform in registers instead of immediates 51.8 %;
+// window table (partly) in registers: no change. Ablations are in profiles/r01_stft_v3.md.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, AID_STFT_MIN_CTAS)
 k_stft(const float* __restrict__ window, const float* __restrict__ twist,
        const float* __restrict__ pcm, const aid_stft_unit* __restrict__ units, int n_units,
@@ -162,7 +164,7 @@ k_stft(const float* __restrict__ window, const float* __restrict__ twist,
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
-        s_win[(i & 31) * kTabStride + (i >> 5)] = window[i];
+        s_win[(i & 31) * kTabStride + (i >> 5)] = 0.5f * window[i];      // exact halving: Z = X_a + i X_b after the mirror sums below
         s_twist[(i >> 5) * kTabStride + (i & 31)] = twist[i];
     }
     __syncthreads();
@@ -233,10 +235,10 @@ k_stft(const float* __restrict__ window, const float* __restrict__ twist,
             const float si = __shfl_sync(AID_FULL_MASK, im[31 - k2], partner);
             const float mr = lane == 0 ? re[(32 - k2) & 31] : sr;
             const float mi = lane == 0 ? im[(32 - k2) & 31] : si;
-            const float ar = zr + mr, ai = zi - mi;      // 2 * X_a[k]
-            const float br = zr - mr, bi = zi + mi;      // 2i * X_b[k]
-            row_a[32 * k2] = log1p_quarter(fmaf(ar, ar, ai * ai));
-            if (has_b) row_a[AID_NBINS + 32 * k2] = log1p_quarter(fmaf(br, br, bi * bi));
+            const float ar = zr + mr, ai = zi - mi;      // X_a[k]   (the window table is pre-scaled by 1/2)
+            const float br = zr - mr, bi = zi + mi;      // i * X_b[k]
+            row_a[32 * k2] = log1p_power(ar, ai);
+            if (has_b) row_a[AID_NBINS + 32 * k2] = log1p_power(br, bi);
         }
         row_a += 2 * AID_NBINS;
 

@@ -17,5 +17,5 @@ for f in stft peaks scan hasher synth index match dedup engine; do
   objs="$objs $o"
 done
 for p in $pids; do wait $p; done
-$NVCC -shared -o ../libaudioident_b200.so $objs -lcudart
+$NVCC -Wno-deprecated-gpu-targets -shared -o ../libaudioident_b200.so $objs -lcudart
 echo built audio_ident_b200/libaudioident_b200.so
