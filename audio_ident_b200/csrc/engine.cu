@@ -20,6 +20,7 @@ extern "C" const char* aid_strerror(int status) {
         case AID_E_IO: return "index directory I/O error";
         case AID_E_FORMAT: return "index files have the wrong format";
         case AID_E_FULL: return "index is full";
+        case AID_E_TIMEOUT: return "a peer rank did not deliver its rows in time";
         default: return "unknown status";
     }
 }

@@ -251,7 +251,7 @@ constexpr int kRankN = 1024;
 
 __global__ void __launch_bounds__(kThreads)
 k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, const aid_seg_desc* __restrict__ segs,
-       int n_seg, int max_rows, aid_match_row* __restrict__ rows, int32_t* __restrict__ n_rows) {
+       int n_seg, int max_rows, aid_match_row* __restrict__ rows, int32_t* __restrict__ n_rows, const RowSink sink) {
     __shared__ uint64_t skey[kRankN];
     __shared__ uint32_t sval[kRankN];       // index of the entry in cand
     __shared__ uint32_t s_fill, s_best;
@@ -295,18 +295,43 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
         __syncthreads();
     }
     const uint32_t n = min(s_best, (uint32_t)max_rows);
+    aid_match_row r;
     if (tid < (int)n) {
         const CandEntry c = cand[sval[tid]];
         const uint32_t sgi = (uint32_t)((sval[tid] / AID_MAX_ROWS) % n_seg);
-        aid_match_row r;
         r.count = (int32_t)(0xffffffffu - c.inv_count);
         r.track = segs[sgi].first_track + (c.key >> AID_POST_T_BITS);
         r.offset = (int32_t)(c.key & ((1u << AID_POST_T_BITS) - 1)) - AID_QUERY_MAX_FRAMES;
         r.q_first = (int32_t)(c.tq & 0xffffu);
         r.q_last = (int32_t)(c.tq >> 16);
-        rows[(int64_t)q * max_rows + tid] = r;
     }
-    if (tid == 0) n_rows[q] = (int32_t)n;
+    if (sink.world == 0) {
+        if (tid < (int)n) rows[(int64_t)q * max_rows + tid] = r;
+        if (tid == 0) n_rows[q] = (int32_t)n;
+        return;
+    }
+    // ---- sharded: deliver the rows, in global track numbers, to every rank's receive window (peer stores over NVLink).
+    // The order inside a rank's block is by local track number; the receiver orders the union by global number.
+    if (tid < (int)n && sink.track_map) r.track = r.track < sink.n_map ? sink.track_map[r.track] : 0xffffffffu;
+    const int parity = (int)(sink.epoch & 1u);
+    for (int p = 0; p < sink.world; p++) {
+        unsigned char* w = sink.window[p];
+        if (tid < (int)n) xchg_rows(w, sink.world, sink.max_q, parity, sink.rank)[(int64_t)q * AID_MAX_ROWS + tid] = r;
+        if (tid == 0) xchg_counts(w, sink.world, sink.max_q, parity, sink.rank)[q] = (int32_t)n;
+    }
+    __threadfence_system();                       // this thread's peer stores are visible system-wide ...
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t prev = atomicAdd(sink.done, 1u);
+        if (prev == gridDim.x - 1) {              // ... so when the last CTA gets here, the whole block is
+            *sink.done = 0;
+            __threadfence_system();
+            for (int p = 0; p < sink.world; p++) {
+                uint32_t* flag = reinterpret_cast<uint32_t*>(sink.window[p]) + sink.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(sink.epoch) : "memory");
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -314,15 +339,22 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
 // Runs the matcher for n_q windows whose fingerprints are on the device: window q owns
 // hash/t[hash_off[q] .. +len), len = hash_len[q] if given, else hash_off[q+1] - hash_off[q].
 // Rows and counts are written to device memory (d_rows[n_q][max_rows], d_n_rows[n_q]); asynchronous on st.
-static int match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
-                            const uint32_t* d_hash_len, const int32_t* d_status, int n_q, aid_match_row* d_rows,
-                            int max_rows, int32_t* d_n_rows, cudaStream_t st) {
+int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
+                         const uint32_t* d_hash_len, const int32_t* d_status, int n_q, aid_match_row* d_rows,
+                         int max_rows, int32_t* d_n_rows, const RowSink& sink, cudaStream_t st) {
     Index* ix = e->index;
     int rc = aid_index_commit_on(e, st);
     if (rc) return rc;
     const int n_seg = (int)ix->segs.size();
     if (n_q == 0) return AID_OK;
-    if (n_seg == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
+    if (n_seg == 0) {
+        if (sink.world == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
+        // an empty shard still has to publish its (empty) block: the peers wait for it
+        k_rank<<<n_q, kThreads, 0, st>>>(nullptr, nullptr, nullptr, 0, max_rows, nullptr, nullptr, sink);
+        AID_CUDA(e, cudaGetLastError());
+        e->launches += 1;
+        return AID_OK;
+    }
     const int64_t n_cta = (int64_t)n_q * n_seg;
     if (n_cta >= ((int64_t)1 << 31)) return AID_E_ARG;
     AID_CUDA(e, ix->cand.ensure((size_t)n_cta * AID_MAX_ROWS * sizeof(CandEntry)));
@@ -332,7 +364,7 @@ static int match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_
                                                   ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>()); }
     { StageTimer tm(e, st, 5);
     k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
-                                     max_rows, d_rows, d_n_rows); }
+                                     max_rows, d_rows, d_n_rows, sink); }
     AID_CUDA(e, cudaGetLastError());
     e->launches += 2;
     return AID_OK;
@@ -346,8 +378,8 @@ static int match_device(aid_engine* e, const uint32_t* d_hash, const uint32_t* d
     if (n_q == 0) return AID_OK;
     AID_CUDA(e, ix->rows.ensure((size_t)n_q * max_rows * sizeof(aid_match_row)));
     AID_CUDA(e, ix->rows_n.ensure((size_t)n_q * 4));
-    int rc = match_device_out(e, d_hash, d_t, d_hash_off, nullptr, d_status, n_q, ix->rows.as<aid_match_row>(), max_rows,
-                              ix->rows_n.as<int32_t>(), st);
+    int rc = aid_match_device_out(e, d_hash, d_t, d_hash_off, nullptr, d_status, n_q, ix->rows.as<aid_match_row>(), max_rows,
+                                  ix->rows_n.as<int32_t>(), RowSink{}, st);
     if (rc) return rc;
     AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.p, (size_t)n_q * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, st));
     AID_CUDA(e, cudaMemcpyAsync(n_rows, ix->rows_n.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
@@ -361,8 +393,8 @@ extern "C" int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32
     if (!e || n_queries < 0 || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
     if (n_queries > 0 && (!d_hash_off || !d_rows || !d_n_rows)) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
-    return match_device_out(e, d_hash, d_t_anchor, d_hash_off, d_hash_len, d_status, n_queries, d_rows, max_rows, d_n_rows,
-                            stream ? (cudaStream_t)stream : e->slot[0].st);
+    return aid_match_device_out(e, d_hash, d_t_anchor, d_hash_off, d_hash_len, d_status, n_queries, d_rows, max_rows, d_n_rows,
+                                RowSink{}, stream ? (cudaStream_t)stream : e->slot[0].st);
 }
 
 extern "C" int aid_copy_device(aid_engine* e, void* d_dst, const void* d_src, int64_t bytes, void* stream) {

@@ -62,6 +62,8 @@ class Engine:
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None):
+            for x in self.__dict__.pop("_exchanges", []):
+                x.close()
             self._L.aid_engine_destroy(self._h)
             self._h = None
 
@@ -102,7 +104,7 @@ class Engine:
         ms = (C.c_double * 8)()
         n = (C.c_int64 * 8)()
         self._check(self._L.aid_engine_stage_times(self._h, ms, n))
-        names = ("stft", "peaks", "compact", "hash", "match", "rank", "index_build")
+        names = ("stft", "peaks", "compact", "hash", "match", "rank", "index_build", "merge")
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(names)}
 
     def params(self) -> dict:
@@ -287,6 +289,20 @@ class Engine:
                                           _ptr(d_status), int(n_queries), _ptr(d_rows), int(max_rows), _ptr(d_n_rows),
                                           _ptr(stream)))
 
+    def exchange(self, rank: int, world: int, max_queries: int) -> "Exchange":
+        """This rank's receive window for sharded identification (aid_exchange_create)."""
+        x = Exchange(self, rank, world, max_queries)
+        self.__dict__.setdefault("_exchanges", []).append(x)
+        return x
+
+    def match_exchange_dev(self, xchg: "Exchange", d_hash, d_t, d_hash_off, d_hash_len, d_status, n_queries: int,
+                           d_track_map, n_map: int, d_rows, d_n_rows, max_rows: int = MAX_ROWS, stream=None) -> None:
+        """aid_match_dev with the ranking kernel storing its rows into every rank's window and a device-side merge:
+        d_rows / d_n_rows receive the merged rows of all ranks (see include/audio_ident_b200.h)."""
+        self._check(self._L.aid_match_exchange_dev(self._h, xchg._h, _ptr(d_hash), _ptr(d_t), _ptr(d_hash_off),
+                                                   _ptr(d_hash_len), _ptr(d_status), int(n_queries), _ptr(d_track_map),
+                                                   int(n_map), _ptr(d_rows), int(max_rows), _ptr(d_n_rows), _ptr(stream)))
+
     def copy_device(self, d_dst, d_src, nbytes: int, stream=None) -> None:
         self._check(self._L.aid_copy_device(self._h, _ptr(d_dst), _ptr(d_src), int(nbytes), _ptr(stream)))
 
@@ -312,3 +328,44 @@ class Engine:
                      stream=None) -> None:
         self._check(self._L.aid_synth_tracks_dev(self._h, _ptr(d_pcm), int(first_track), int(n_tracks),
                                                  int(samples_per_track), int(seed), _ptr(stream)))
+
+
+class Exchange:
+    """Receive window of one rank for the fused rank + exchange path (include/audio_ident_b200.h, aid_exchange_*)."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, engine: Engine, rank: int, world: int, max_queries: int):
+        self.engine, self.rank, self.world, self.max_queries = engine, int(rank), int(world), int(max_queries)
+        h = C.c_void_p()
+        engine._check(engine._L.aid_exchange_create(engine._h, self.rank, self.world, self.max_queries, C.byref(h)))
+        self._h = h
+
+    def handle(self) -> bytes:
+        buf = (C.c_uint8 * self.HANDLE_BYTES)()
+        self.engine._check(self.engine._L.aid_exchange_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles: Sequence[bytes]) -> None:
+        """handles: one 64-byte handle per rank, in rank order (processes on the same box)."""
+        if len(handles) != self.world or any(len(h) != self.HANDLE_BYTES for h in handles):
+            raise ValueError("one 64-byte handle per rank")
+        blob = (C.c_uint8 * (self.HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(handles))
+        self.engine._check(self.engine._L.aid_exchange_connect(self._h, blob))
+
+    def connect_local(self, peers: Sequence["Exchange"]) -> None:
+        """peers: the Exchange objects of all ranks, in rank order, living in this process."""
+        arr = (C.c_void_p * self.world)(*[p._h for p in peers])
+        self.engine._check(self.engine._L.aid_exchange_connect_local(self._h, arr))
+
+    def set_timeout_ms(self, ms: int) -> None:
+        self.engine._check(self.engine._L.aid_exchange_set_timeout_ms(self._h, int(ms)))
+
+    def check(self) -> None:
+        """Raises if a merge gave up waiting for a peer (synchronises the device)."""
+        self.engine._check(self.engine._L.aid_exchange_status(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self.engine._L.aid_exchange_destroy(self._h)
+            self._h = None

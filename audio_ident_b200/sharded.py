@@ -72,6 +72,14 @@ def merge_rows(blocks):
     return merged, n_rows
 
 
+def connect_local(identifiers) -> None:
+    """Wires the peer exchanges of ranks that live in one process (each created with
+    enable_peer_exchange(..., connect=False)), in rank order."""
+    xs = [sh._xchg for sh in identifiers]
+    for x in xs:
+        x.connect_local(xs)
+
+
 class ShardedIdentifier:
     """`backend` is an audio_ident_b200.engine.Engine (or anything with the same index_add / query /
     query_hashes methods, which is how the CPU gloo tests drive the exchange logic). With `device` set (a torch
@@ -81,7 +89,33 @@ class ShardedIdentifier:
         self.backend, self.rank, self.world, self.group, self.device = backend, rank, world, group, device
         self.to_global: list[int] = []          # local track number -> global track number
         self._to_global_dev = None
+        self._map_dev = None                    # the same table as int32 for the fused exchange kernels
         self._stream = None
+        self._xchg = None                       # engine.Exchange once enable_peer_exchange() ran
+
+    # ---- fused rank + exchange over peer memory (include/audio_ident_b200.h, aid_exchange_*)
+    def enable_peer_exchange(self, max_queries: int, connect: bool = True) -> None:
+        """Replaces "all-gather the 50-row blocks with NCCL, sort them with torch" by the engine's own exchange:
+        k_rank stores its rows into every rank's receive window over NVLink, k_merge_blocks merges on the device.
+        One process per GPU: the 64-byte IPC handles travel once through torch.distributed; ranks living in one
+        process (tests) pass connect=False and call sharded.connect_local([...]) afterwards."""
+        if self.device is None or not hasattr(self.backend, "exchange"):
+            raise RuntimeError("the peer exchange needs CUDA engines")
+        self._xchg = self.backend.exchange(self.rank, self.world, int(max_queries))
+        if connect and self.world > 1:
+            import torch.distributed as dist
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self._xchg.handle(), group=self.group)
+            self._xchg.connect(handles)
+            dist.barrier(group=self.group)
+
+    def _rows_out(self, rows, nrows):
+        """int32 [n, 50, 5] merged rows + counts from the engine -> the (int64 rows with -1 fill, n_rows) merge_rows returns."""
+        import torch
+        valid = torch.arange(MAX_ROWS, device=rows.device)[None, :] < nrows[:, None]
+        r64 = rows.to(torch.int64)
+        r64[:, :, 1] &= 0xFFFFFFFF
+        return torch.where(valid[:, :, None], r64, torch.full_like(r64, -1)), nrows
 
     # ---- ingest: no collective
     def my_tracks(self, n_global: int, first: int = 0) -> list[int]:
@@ -92,6 +126,7 @@ class ShardedIdentifier:
         assert not self.to_global or not len(global_ids) or global_ids[0] > self.to_global[-1], "add in increasing global order"
         self.to_global.extend(int(g) for g, k in zip(global_ids, ok) if k)      # a refused track gets no local number
         self._to_global_dev = None
+        self._map_dev = None
 
     def add(self, pcm, sample_off, global_ids: Sequence[int], device: bool = False) -> np.ndarray:
         ok = self.backend.index_add(pcm, sample_off, [str(g) for g in global_ids], device=device)
@@ -162,9 +197,16 @@ class ShardedIdentifier:
             lens_all = torch.cat([metas[q, 1 + per:1 + per + bounds[q + 1] - bounds[q]] for q in range(P)]).contiguous()
             rows = torch.empty((n, MAX_ROWS, 5), **i32)
             nrows = torch.empty(n, **i32)
-            self.backend.match_dev(allb.data_ptr(), allb.data_ptr() + 4 * cap, begins, lens_all, None, n, rows, nrows,
-                                   MAX_ROWS, st)
-            out = self._merge_device(rows, nrows)
+            if self._xchg is not None and n <= self._xchg.max_queries:
+                if self._map_dev is None:
+                    self._map_dev = torch.tensor(self.to_global if self.to_global else [0], **i32)
+                self.backend.match_exchange_dev(self._xchg, allb.data_ptr(), allb.data_ptr() + 4 * cap, begins, lens_all,
+                                                None, n, self._map_dev, len(self.to_global), rows, nrows, MAX_ROWS, st)
+                out = self._rows_out(rows, nrows)
+            else:
+                self.backend.match_dev(allb.data_ptr(), allb.data_ptr() + 4 * cap, begins, lens_all, None, n, rows, nrows,
+                                       MAX_ROWS, st)
+                out = self._merge_device(rows, nrows)
         torch.cuda.current_stream(self.device).wait_stream(self._stream)
         return out
 

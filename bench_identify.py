@@ -43,6 +43,9 @@ def main():
     ap.add_argument("--snr-db", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ingest-chunk", type=int, default=512)
+    ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer",
+                    help="peer: k_rank stores rows into every rank's window over NVLink + device merge (aid_match_exchange_dev); "
+                         "nccl: all-gather of 50-row blocks + torch sort (the earlier path, kept for comparison)")
     args = ap.parse_args()
 
     import torch
@@ -112,6 +115,9 @@ def main():
     off = np.arange(n_win + 1, dtype=np.int64) * 56000
     torch.cuda.synchronize()
 
+    if args.exchange == "peer":
+        sh.enable_peer_exchange(n_win)
+
     def step():
         return sh.query(wins.data_ptr(), off, device=True)
 
@@ -120,17 +126,24 @@ def main():
     barrier()
     eng.stage_times(); eng.set_stage_timing(True)
     launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record()                                   # the step's own stream waits for / is waited on by this one
     for _ in range(args.steps):
         merged, n = step()
+    ev1.record()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt_wall = time.perf_counter() - t0
+    dt_dev = ev0.elapsed_time(ev1) * 1e-3
+    if sh._xchg is not None:
+        sh._xchg.check()
     stage = eng.stage_times(); eng.set_stage_timing(False)
     launches = eng.launches - launches0
-    t_all = torch.tensor([dt], dtype=torch.float64, device=dev)
+    t_all = torch.tensor([dt_dev, dt_wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    dt = float(t_all.item()) / args.steps
+    dt = float(t_all[0].item()) / args.steps        # CUDA events on the launching stream, max over ranks
+    dt_wall = float(t_all[1].item()) / args.steps
     qps = args.queries / dt
 
     # ---- accuracy in the reference's terms: sum aligned hashes per track over the three windows, top-1
@@ -163,7 +176,9 @@ def main():
             "config": {"workload": f"identify {args.queries} x 5 s queries (3 x 3.5 s windows, {args.snr_db:g} dB SNR) "
                                    f"against {args.tracks} x {args.seconds:g} s tracks", "index_sharding": f"track g on rank g % {world}",
                        "windows_per_step": n_win},
-            "timed_region": "device-resident query PCM -> fingerprint -> probe/vote -> rows to host -> all-gather -> merge (wall clock, max over ranks)",
+            "timed_region": "device-resident query PCM -> fingerprint -> hash all-gather -> probe/vote/rank -> row exchange -> "
+                            "merged rows on every rank (CUDA events, max over ranks; wall clock beside it)",
+            "exchange": args.exchange, "ms_per_step_wall": dt_wall * 1e3,
             "top1_accuracy": top1 / args.queries, "top1_offset_within_1_frame": offs_ok / max(top1, 1),
             "rows_digest": digest, "index": {"tracks_per_rank": stats["tracks"], "postings_per_rank": stats["postings"],
                                              "segments_per_rank": stats["segments"], "device_bytes_per_rank": stats["device_bytes"],

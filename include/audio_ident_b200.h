@@ -33,7 +33,8 @@ typedef enum {
     AID_E_NOT_FOUND = -5,   /* unknown track name */
     AID_E_IO = -6,          /* index directory could not be read or written */
     AID_E_FORMAT = -7,      /* index files are not ours / wrong version */
-    AID_E_FULL = -8         /* index limits reached */
+    AID_E_FULL = -8,        /* index limits reached */
+    AID_E_TIMEOUT = -9      /* sharded identification: a peer rank did not deliver its rows in time */
 } aid_status;
 
 /* per-track status bits written by the fingerprint stages */
@@ -75,7 +76,8 @@ int         aid_engine_sync(aid_engine* e);
 int         aid_engine_set_max_batch_frames(aid_engine* e, int64_t frames);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's roofline numbers).
  * Stages: 0 = STFT kernel, 1 = peak kernel, 2 = peak compaction (scan + copy), 3 = hasher (count + scan +
- * write), 4 = matcher (k_match), 5 = ranking (k_rank), 6 = index build, 7 = unused.
+ * write), 4 = matcher (k_match), 5 = ranking (k_rank, with its peer stores when sharded), 6 = index build,
+ * 7 = merge of the ranks' row blocks (k_merge_blocks, including the wait for the slowest rank).
  * aid_engine_stage_times waits for the recorded work, adds the elapsed milliseconds and the number
  * of timed launches per stage into ms[8] / launches[8], and forgets the records. */
 int         aid_engine_set_stage_timing(aid_engine* e, int on);
@@ -163,6 +165,39 @@ int aid_query_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anch
 int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t_anchor, const uint32_t* d_hash_off,
                   const uint32_t* d_hash_len, const int32_t* d_status, int n_queries,
                   aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream);
+
+/* ---- sharded identification: ranking fused with the row exchange over peer memory ----
+ * The reference has one index, so one `olaf_c query` (fingerprint.py:185-193) sees every track. With the index
+ * sharded over the GPUs of a box (one process per GPU, each with its own engine) every rank probes its shard for
+ * the same windows and the rows have to meet. An aid_exchange is this rank's receive window in its own HBM;
+ * after the ranks have swapped the 64-byte handles (any transport: torch.distributed, a pipe ...) each rank's
+ * ranking kernel stores its rows, renumbered to global track numbers, straight into every rank's window over
+ * NVLink and a merge kernel on each rank waits for all blocks on the device and orders their union by
+ * (count desc, global track asc, offset asc), keeping max_rows: the same rows on every rank, identical to one
+ * unsharded index. No collective call and no host synchronisation.
+ * All ranks must call aid_match_exchange_dev with the same window batch, the same number of times, and each rank
+ * always on the same stream. AID_MAX_RANKS = GPUs of one NVSwitch box. */
+#define AID_MAX_RANKS 8
+#define AID_IPC_HANDLE_BYTES 64
+typedef struct aid_exchange aid_exchange;
+int  aid_exchange_create(aid_engine* e, int rank, int world, int max_queries, aid_exchange** out);
+void aid_exchange_destroy(aid_exchange* x);
+/* handle[64] of this rank's window for ranks in other processes (a cudaIpcMemHandle_t) */
+int  aid_exchange_handle(aid_exchange* x, uint8_t* handle);
+/* handles[world][64] of all ranks in rank order (this rank's own entry is ignored) */
+int  aid_exchange_connect(aid_exchange* x, const uint8_t* handles);
+/* ranks living in this process (one process driving several engines; tests): peers[world] */
+int  aid_exchange_connect_local(aid_exchange* x, aid_exchange* const* peers);
+/* how long the merge kernel waits for the slowest rank before it gives up (default 20 s) */
+int  aid_exchange_set_timeout_ms(aid_exchange* x, int64_t ms);
+/* AID_OK, or AID_E_TIMEOUT if a merge gave up waiting (n_rows of its windows are -1); synchronises */
+int  aid_exchange_status(aid_exchange* x);
+/* aid_match_dev + exchange + merge. d_track_map[n_map] (device, may be NULL) maps this engine's track numbers to
+ * global ones; d_rows[n_queries][max_rows] / d_n_rows[n_queries] receive the merged rows. Asynchronous on stream. */
+int  aid_match_exchange_dev(aid_engine* e, aid_exchange* x, const uint32_t* d_hash, const uint32_t* d_t_anchor,
+                            const uint32_t* d_hash_off, const uint32_t* d_hash_len, const int32_t* d_status,
+                            int n_queries, const uint32_t* d_track_map, int64_t n_map, aid_match_row* d_rows,
+                            int max_rows, int32_t* d_n_rows, void* stream);
 
 /* ---- content-duplicate scan ----------------------------------------------
  * Replaces the per-row Python loop of audio-ident-service/app/audio/dedup.py:170-222 (check_content_duplicate)

@@ -64,3 +64,141 @@ def test_device_resident_query_path_equals_host_path(engine, oracle):
         assert np.array_equal(m[q, :n[q]], ref[q, :n[q]]), q
     assert (n[:9] >= 1).all() and n[9] == 0
     engine.index_clear()
+
+
+def _device_fingerprints(engine, torch, qp, qo):
+    """query windows -> (hash, t_anchor, hash_off u32) as torch tensors that outlive the engine's buffers"""
+    n = len(qo) - 1
+    d = torch.from_numpy(qp).cuda()
+    res = engine.fingerprint_dev(d.data_ptr(), qo)
+    off = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    engine.copy_device(off, res.d_hash_off, 4 * (n + 1))
+    engine.sync()
+    total = int(off[-1].item())
+    h = torch.zeros(max(total, 1), dtype=torch.int32, device="cuda")
+    t = torch.zeros(max(total, 1), dtype=torch.int32, device="cuda")
+    engine.copy_device(h, res.d_hash, 4 * total)
+    engine.copy_device(t, res.d_t_anchor, 4 * total)
+    engine.sync()
+    return h, t, off
+
+
+def test_fused_rank_exchange_equals_one_index(engine):
+    """aid_match_exchange_dev: three engines on one GPU stand in for three ranks (tracks g % 3 == r); k_rank stores
+    its rows into every rank's window, k_merge_blocks merges.
+    Every rank must end up with the rows of one unsharded index, over several epochs (the windows are
+    double-buffered by epoch parity)."""
+    torch = pytest.importorskip("torch")
+    tracks = [synth.make_track(900 + k, 10.0) for k in range(9)]
+    tracks += [tracks[2].copy(), tracks[2].copy(), tracks[2].copy()]          # duplicates: one on each rank
+    engine.index_clear()
+    pcm, off = ragged(tracks)
+    assert engine.index_add(pcm, off, [str(g) for g in range(len(tracks))]).all()
+    W = 3
+    ranks = []
+    try:
+        for r in range(W):
+            e = Engine(0)
+            sh = sharded.ShardedIdentifier(e, r, W, device=torch.device("cuda", 0))
+            mine = sh.my_tracks(len(tracks))
+            p2, o2 = ragged([tracks[g] for g in mine])
+            assert sh.add(p2, o2, mine).all()
+            e.index_commit()
+            ranks.append((e, sh))
+        for epoch in range(3):
+            wins = []
+            for q in range(6):
+                clip, _ = synth.make_query(tracks[(q + epoch) % 9], 70 + q + 10 * epoch, 5.0, 20.0)
+                wins += [clip[:56000], clip[12000:68000], clip[24000:]]
+            wins.append(np.zeros(200, np.float32))                               # a window without fingerprints
+            qp, qo = ragged(wins)
+            n = len(wins)
+            rows1, n1 = engine.query(qp, qo)
+            single = sharded.rows_to_array(rows1, n1, np.arange(len(tracks)))
+            h, t, hoff = _device_fingerprints(engine, torch, qp, qo)
+            if epoch == 0:
+                for e, sh in ranks:
+                    sh.enable_peer_exchange(64, connect=False)
+                sharded.connect_local([sh for _, sh in ranks])
+            outs = []
+            streams = [torch.cuda.Stream() for _ in ranks]
+            for (e, sh), st in zip(ranks, streams):                                # nobody waits on the host in between
+                rows = torch.empty((n, 50, 5), dtype=torch.int32, device="cuda")
+                nrows = torch.empty(n, dtype=torch.int32, device="cuda")
+                tmap = torch.tensor(sh.to_global, dtype=torch.int32, device="cuda")
+                e.match_exchange_dev(sh._xchg, h, t, hoff, None, None, n, tmap, len(sh.to_global), rows, nrows, 50,
+                                     st.cuda_stream)
+                outs.append((rows, nrows, tmap))
+            torch.cuda.synchronize()
+            for (e, sh), (rows, nrows, _) in zip(ranks, outs):
+                sh._xchg.check()
+                nn = nrows.cpu().numpy()
+                assert np.array_equal(nn, n1)
+                m = rows.cpu().numpy().astype(np.int64)
+                for q in range(n):
+                    assert np.array_equal(m[q, :nn[q]], single[q, :nn[q]]), (epoch, sh.rank, q)
+            assert (n1[:18] >= 1).all() and n1[18] == 0
+            if epoch == 0:                          # query 2 is the triplicated track: rows from all three ranks interleave
+                assert n1[6] >= 4 and {int(x) for x in single[6, :4, 1]} == {2, 9, 10, 11}
+    finally:
+        for e, _ in ranks:
+            e.close()
+        engine.index_clear()
+
+
+def test_fused_exchange_single_rank_and_timeout(engine):
+    """world 1: the fused path equals aid_match_dev. world 2 with a silent peer: the merge gives up after the
+    timeout, reports AID_E_TIMEOUT and marks the windows (-1) instead of inventing rows."""
+    torch = pytest.importorskip("torch")
+    from audio_ident_b200.engine import EngineError
+    tracks = [synth.make_track(950 + k, 8.0) for k in range(4)]
+    engine.index_clear()
+    pcm, off = ragged(tracks)
+    assert engine.index_add(pcm, off, [str(g) for g in range(4)]).all()
+    wins = [tracks[k % 4][3000 * k:3000 * k + 56000] for k in range(5)]
+    qp, qo = ragged(wins)
+    n = len(wins)
+    h, t, hoff = _device_fingerprints(engine, torch, qp, qo)
+    ref = torch.empty((n, 50, 5), dtype=torch.int32, device="cuda"); ref_n = torch.empty(n, dtype=torch.int32, device="cuda")
+    engine.match_dev(h, t, hoff, None, None, n, ref, ref_n)
+    x1 = engine.exchange(0, 1, 16)
+    rows = torch.empty((n, 50, 5), dtype=torch.int32, device="cuda"); nrows = torch.empty(n, dtype=torch.int32, device="cuda")
+    engine.match_exchange_dev(x1, h, t, hoff, None, None, n, None, 0, rows, nrows)
+    engine.sync(); torch.cuda.synchronize()
+    x1.check()
+    nn = nrows.cpu().numpy()
+    assert np.array_equal(nn, ref_n.cpu().numpy()) and (nn >= 1).all()
+    a, b = rows.cpu().numpy(), ref.cpu().numpy()
+    for q in range(n):
+        assert np.array_equal(a[q, :nn[q]], b[q, :nn[q]])
+    x1.close()
+
+    # world 2 where rank 1's shard is empty: it still publishes its (empty) blocks and both ranks see rank 0's rows
+    with Engine(0) as empty:
+        xa, xb = engine.exchange(0, 2, 16), empty.exchange(1, 2, 16)
+        xa.connect_local([xa, xb]); xb.connect_local([xa, xb])
+        rows_b = torch.empty((n, 50, 5), dtype=torch.int32, device="cuda"); nrows_b = torch.empty(n, dtype=torch.int32, device="cuda")
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        engine.match_exchange_dev(xa, h, t, hoff, None, None, n, None, 0, rows, nrows, 50, sa.cuda_stream)
+        empty.match_exchange_dev(xb, h, t, hoff, None, None, n, None, 0, rows_b, nrows_b, 50, sb.cuda_stream)
+        torch.cuda.synchronize()
+        xa.check(); xb.check()
+        for rr, nr_ in ((rows, nrows), (rows_b, nrows_b)):
+            assert np.array_equal(nr_.cpu().numpy(), nn)
+            a = rr.cpu().numpy()
+            for q in range(n):
+                assert np.array_equal(a[q, :nn[q]], b[q, :nn[q]])
+        xa.close(); xb.close()
+
+    x2 = engine.exchange(0, 2, 16)
+    peer = engine.exchange(1, 2, 16)                   # exists, never publishes
+    x2.connect_local([x2, peer]); peer.connect_local([x2, peer])
+    x2.set_timeout_ms(100)
+    engine.match_exchange_dev(x2, h, t, hoff, None, None, n, None, 0, rows, nrows)
+    engine.sync()
+    with pytest.raises(EngineError) as ei:
+        x2.check()
+    assert ei.value.status == -9
+    assert (nrows.cpu().numpy() == -1).all()
+    x2.close(); peer.close()
+    engine.index_clear()
