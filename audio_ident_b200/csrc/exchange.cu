@@ -13,6 +13,12 @@
 // straight into all of them while it is ranking the next windows: only the rows that exist cross NVLink (a handful
 // per window instead of 1000 B), there is no collective call and no host synchronisation. k_merge_blocks then waits,
 // on the device, for the epoch flags of all ranks and merges the blocks, one warp per window.
+//
+// aid_identify_exchange_dev runs the whole step that way: rank r fingerprints its slice of the window batch,
+// k_publish_hashes stores those fingerprints into every rank's window (instead of an all-gather padded to the largest
+// rank, whose size needed a host synchronisation), k_wait_hashes holds the stream until all slices have arrived,
+// then probe/vote, the fused ranking + row stores, and the merge.
+#include <algorithm>
 #include <cstring>
 #include "engine.h"
 #include "index.h"
@@ -20,13 +26,15 @@
 struct aid_exchange {
     aid_engine* e = nullptr;
     int rank = 0, world = 0, max_q = 0;
+    XchgLayout lay;
     unsigned char* window = nullptr;                 // this rank's receive window
     unsigned char* peer[AID_MAX_RANKS] = {};
     bool ipc_open[AID_MAX_RANKS] = {};
     bool connected = false;
     uint32_t epoch = 0;
-    uint32_t* d_done = nullptr;                      // [0] = k_rank completion counter, [1] = error word
+    uint32_t* d_done = nullptr;                      // [0] k_rank counter, [1] timeout seen, [2] hash capacity exceeded, [3] publish counter
     int64_t timeout_ms = 20000;
+    int clock_khz = 2000000;                         // SM clock for the timeout (queried once: the attribute is slow)
 };
 
 namespace {
@@ -34,10 +42,79 @@ namespace {
 constexpr int kMergeWarps = 4;
 constexpr int kMergeCap = AID_MAX_RANKS * AID_MAX_ROWS;
 
+// spins until *flag has reached `epoch` (flags only grow; a peer may already be one epoch ahead)
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch, long long timeout_cycles) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - epoch) >= 0) return true;
+        if (clock64() - t0 > timeout_cycles) return false;
+        __nanosleep(100);
+    }
+}
+
+// ---- query fingerprints of this rank's slice of the batch -> every rank's window
+struct HashSink {
+    XchgLayout lay;
+    int rank = 0;
+    uint32_t epoch = 0;
+    unsigned char* window[AID_MAX_RANKS] = {};
+    uint32_t* done = nullptr;                  // CTA completion counter (local)
+};
+
+__global__ void __launch_bounds__(256)
+k_publish_hashes(const uint32_t* __restrict__ hash, const uint32_t* __restrict__ t, const uint32_t* __restrict__ hash_off,
+                 const int32_t* __restrict__ status, int count, int first_window, const HashSink sink) {
+    const int parity = (int)(sink.epoch & 1u), P = sink.lay.world;
+    const uint32_t total = count > 0 ? hash_off[count] : 0u;
+    const bool fits = total <= sink.lay.hcap;
+    const size_t slot = (size_t)sink.rank * sink.lay.hcap;
+    const uint32_t stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fits)
+        for (uint32_t i = i0; i < total; i += stride) {
+            const uint32_t h = hash[i], tt = t[i];
+            for (int p = 0; p < P; p++) {
+                sink.lay.hash(sink.window[p], parity)[slot + i] = h;
+                sink.lay.t(sink.window[p], parity)[slot + i] = tt;
+            }
+        }
+    for (uint32_t j = i0; j < (uint32_t)count; j += stride) {
+        const uint32_t b = hash_off[j], len = fits && (status[j] & 3) == 0 ? hash_off[j + 1] - b : 0u;
+        for (int p = 0; p < P; p++) {
+            sink.lay.begins(sink.window[p], parity)[first_window + j] = (uint32_t)slot + b;
+            sink.lay.lens(sink.window[p], parity)[first_window + j] = len;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(sink.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *sink.done = 0;
+            __threadfence_system();
+            for (int p = 0; p < P; p++) {
+                XchgLayout::hash_status(sink.window[p])[sink.rank] = fits ? 0u : 1u;     // 1: slice larger than hcap
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(XchgLayout::hash_flag(sink.window[p]) + sink.rank),
+                             "r"(sink.epoch) : "memory");
+            }
+        }
+    }
+}
+
+// one warp holds the stream until every rank's fingerprints of this epoch are in this rank's window
+__global__ void k_wait_hashes(unsigned char* window, int world, uint32_t epoch, uint32_t* err, long long timeout_cycles) {
+    const int lane = threadIdx.x;
+    if (lane >= world) return;
+    if (!wait_flag(XchgLayout::hash_flag(window) + lane, epoch, timeout_cycles)) { atomicExch(err, 1u); return; }
+    if (XchgLayout::hash_status(window)[lane] != 0) atomicExch(err + 1, 1u);
+}
+
 __global__ void __launch_bounds__(kMergeWarps * 32)
-k_merge_blocks(unsigned char* __restrict__ window, int world, int max_q, uint32_t epoch, int n_q, int max_rows,
+k_merge_blocks(unsigned char* __restrict__ window, const XchgLayout lay, uint32_t epoch, int n_q, int max_rows,
                aid_match_row* __restrict__ rows, int32_t* __restrict__ n_rows, uint32_t* __restrict__ err,
                long long timeout_cycles) {
+    const int world = lay.world;
     __shared__ uint64_t s_key[kMergeWarps][kMergeCap];      // (0xffffffff - count) << 32 | global track
     __shared__ int32_t s_off[kMergeWarps][kMergeCap];
     __shared__ uint16_t s_src[kMergeWarps][kMergeCap];      // source rank << 6 | row
@@ -49,15 +126,7 @@ k_merge_blocks(unsigned char* __restrict__ window, int world, int max_q, uint32_
     // every rank's block of this epoch has to be complete: lane p watches the flag rank p publishes
     bool ok = true;
     if (lane < world) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(window) + lane;
-        const long long t0 = clock64();
-        for (;;) {
-            uint32_t v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if ((int32_t)(v - epoch) >= 0) break;
-            if (clock64() - t0 > timeout_cycles) { ok = false; break; }
-            __nanosleep(100);
-        }
+        ok = wait_flag(XchgLayout::row_flag(window) + lane, epoch, timeout_cycles);
     }
     if (!__all_sync(AID_FULL_MASK, ok)) {                    // a peer never delivered: report, do not invent rows
         if (lane == 0) { atomicExch(err, 1u); n_rows[q] = -1; }
@@ -65,7 +134,7 @@ k_merge_blocks(unsigned char* __restrict__ window, int world, int max_q, uint32_
     }
 
     const int parity = (int)(epoch & 1u);
-    const int cnt = lane < world ? min(max(xchg_counts(window, world, max_q, parity, lane)[q], 0), AID_MAX_ROWS) : 0;
+    const int cnt = lane < world ? min(max(lay.counts(window, parity, lane)[q], 0), AID_MAX_ROWS) : 0;
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -75,7 +144,7 @@ k_merge_blocks(unsigned char* __restrict__ window, int world, int max_q, uint32_
     const int total = __shfl_sync(AID_FULL_MASK, incl, 31);
     for (int p = 0; p < world; p++) {
         const int c = __shfl_sync(AID_FULL_MASK, cnt, p), b = __shfl_sync(AID_FULL_MASK, incl - cnt, p);
-        const aid_match_row* src = xchg_rows(window, world, max_q, parity, p) + (int64_t)q * AID_MAX_ROWS;
+        const aid_match_row* src = lay.rows(window, parity, p) + (int64_t)q * AID_MAX_ROWS;
         for (int i = lane; i < c; i += 32) {
             const aid_match_row r = src[i];
             s_key[warp][b + i] = (uint64_t)(0xffffffffu - (uint32_t)r.count) << 32 | r.track;
@@ -96,7 +165,7 @@ k_merge_blocks(unsigned char* __restrict__ window, int world, int max_q, uint32_
         if (pos < max_rows) {
             const int s = s_src[warp][i];
             rows[(int64_t)q * max_rows + pos] =
-                (xchg_rows(window, world, max_q, parity, s >> 6) + (int64_t)q * AID_MAX_ROWS)[s & 63];
+                (lay.rows(window, parity, s >> 6) + (int64_t)q * AID_MAX_ROWS)[s & 63];
         }
     }
     if (lane == 0) n_rows[q] = min(total, max_rows);
@@ -107,16 +176,21 @@ int fail(aid_exchange* x, cudaError_t ce, const char* what) { return aid_fail_cu
 
 }  // namespace
 
-extern "C" int aid_exchange_create(aid_engine* e, int rank, int world, int max_queries, aid_exchange** out) {
-    if (!e || !out || world < 1 || world > AID_MAX_RANKS || rank < 0 || rank >= world || max_queries < 1) return AID_E_ARG;
+extern "C" int aid_exchange_create(aid_engine* e, int rank, int world, int max_queries, int64_t max_hashes_per_rank,
+                                   aid_exchange** out) {
+    if (!e || !out || world < 1 || world > AID_MAX_RANKS || rank < 0 || rank >= world || max_queries < 1 ||
+        max_hashes_per_rank < 0 || max_hashes_per_rank >= ((int64_t)1 << 28)) return AID_E_ARG;
+    if (max_hashes_per_rank == 0)        // default: 1024 per window of a rank's slice (a 3.5 s window has ~300)
+        max_hashes_per_rank = std::min<int64_t>(((int64_t)max_queries + world - 1) / world * 1024, ((int64_t)1 << 28) - 1);
     AID_CUDA(e, cudaSetDevice(e->device));
     aid_exchange* x = new aid_exchange();
     x->e = e; x->rank = rank; x->world = world; x->max_q = max_queries;
-    const size_t bytes = xchg_window_bytes(world, max_queries);
+    x->lay = XchgLayout::make(world, max_queries, (uint32_t)max_hashes_per_rank);
+    const size_t bytes = x->lay.bytes;
     cudaError_t ce = cudaMalloc(&x->window, bytes);          // a plain cudaMalloc: IPC cannot export pool memory
     if (ce == cudaSuccess) ce = cudaMemset(x->window, 0, bytes);
-    if (ce == cudaSuccess) ce = cudaMalloc(&x->d_done, 8);
-    if (ce == cudaSuccess) ce = cudaMemset(x->d_done, 0, 8);
+    if (ce == cudaSuccess) ce = cudaMalloc(&x->d_done, 16);      // [0] k_rank counter, [1] timeout, [2] capacity, [3] publish counter
+    if (ce == cudaSuccess) ce = cudaMemset(x->d_done, 0, 16);
     if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) {
         if (x->window) cudaFree(x->window);
@@ -124,6 +198,9 @@ extern "C" int aid_exchange_create(aid_engine* e, int rank, int world, int max_q
         delete x;
         return aid_fail_cuda(e, ce, "aid_exchange_create");
     }
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device) == cudaSuccess && khz > 0) x->clock_khz = khz;
+    else cudaGetLastError();
     x->peer[rank] = x->window;
     x->connected = world == 1;
     *out = x;
@@ -195,12 +272,37 @@ extern "C" int aid_exchange_set_timeout_ms(aid_exchange* x, int64_t ms) {
 extern "C" int aid_exchange_status(aid_exchange* x) {
     if (!x) return AID_E_ARG;
     X_CUDA(x, cudaSetDevice(x->e->device));
-    uint32_t err = 0;
-    X_CUDA(x, cudaMemcpy(&err, x->d_done + 1, 4, cudaMemcpyDeviceToHost));
-    if (err) {
-        x->e->err = "a peer rank did not deliver its rows within the exchange timeout";
+    uint32_t err[2] = {0, 0};
+    X_CUDA(x, cudaMemcpy(err, x->d_done + 1, 8, cudaMemcpyDeviceToHost));
+    if (err[0]) {
+        x->e->err = "a peer rank did not deliver its block within the exchange timeout";
         return AID_E_TIMEOUT;
     }
+    if (err[1]) {
+        x->e->err = "a rank's query fingerprints exceed max_hashes_per_rank of the exchange";
+        return AID_E_CAPACITY;
+    }
+    return AID_OK;
+}
+
+// probe/vote + ranking with the row stores into every window (match.cu), then the merge of all ranks' blocks
+static int match_and_merge(aid_engine* e, aid_exchange* x, uint32_t epoch, const uint32_t* d_hash, const uint32_t* d_t,
+                           const uint32_t* d_hash_off, const uint32_t* d_hash_len, const int32_t* d_status, int n_q,
+                           const uint32_t* d_track_map, int64_t n_map, aid_match_row* d_rows, int max_rows,
+                           int32_t* d_n_rows, cudaStream_t st) {
+    RowSink sink;
+    sink.lay = x->lay; sink.rank = x->rank; sink.epoch = epoch;
+    for (int p = 0; p < x->world; p++) sink.window[p] = x->peer[p];
+    sink.done = x->d_done;
+    sink.track_map = d_track_map; sink.n_map = (uint32_t)n_map;
+    int rc = aid_match_device_out(e, d_hash, d_t, d_hash_off, d_hash_len, d_status, n_q, nullptr, max_rows, nullptr, sink, st);
+    if (rc) return rc;
+    const long long timeout_cycles = (long long)x->timeout_ms * x->clock_khz;
+    { StageTimer tm(e, st, 7);
+    k_merge_blocks<<<(n_q + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, 0, st>>>(
+        x->window, x->lay, epoch, n_q, max_rows, d_rows, d_n_rows, x->d_done + 1, timeout_cycles); }
+    AID_CUDA(e, cudaGetLastError());
+    e->launches += 1;
     return AID_OK;
 }
 
@@ -214,22 +316,38 @@ extern "C" int aid_match_exchange_dev(aid_engine* e, aid_exchange* x, const uint
     if (n_queries == 0) return AID_OK;               // nothing to publish: every rank passes the same batch
     AID_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->slot[0].st;
-    RowSink sink;
-    sink.world = x->world; sink.rank = x->rank; sink.max_q = x->max_q;
-    sink.epoch = ++x->epoch;
-    for (int p = 0; p < x->world; p++) sink.window[p] = x->peer[p];
-    sink.done = x->d_done;
-    sink.track_map = d_track_map; sink.n_map = (uint32_t)n_map;
-    int rc = aid_match_device_out(e, d_hash, d_t_anchor, d_hash_off, d_hash_len, d_status, n_queries, nullptr, max_rows,
-                                  nullptr, sink, st);
+    return match_and_merge(e, x, ++x->epoch, d_hash, d_t_anchor, d_hash_off, d_hash_len, d_status, n_queries, d_track_map,
+                           n_map, d_rows, max_rows, d_n_rows, st);
+}
+
+extern "C" int aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const float* d_pcm, const int64_t* sample_off,
+                                         int n_windows, const uint32_t* d_track_map, int64_t n_map,
+                                         aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream) {
+    if (!e || !x || x->e != e || !x->connected || !sample_off || n_windows < 0 || n_windows > x->max_q || max_rows < 1 ||
+        max_rows > AID_MAX_ROWS || n_map < 0 || n_map >= ((int64_t)1 << 32)) return AID_E_ARG;
+    if (n_windows > 0 && (!d_rows || !d_n_rows)) return AID_E_ARG;
+    if (n_windows == 0) return AID_OK;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->slot[0].st;
+    const int P = x->world, r = x->rank;
+    const int lo = (int)((int64_t)r * n_windows / P), hi = (int)((int64_t)(r + 1) * n_windows / P);
+    aid_fp_device_result fp{};
+    int rc = aid_fingerprint_dev(e, d_pcm, sample_off + lo, hi - lo, &fp, st);     // this rank's slice only
     if (rc) return rc;
-    int clock_khz = 0;
-    AID_CUDA(e, cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, e->device));
-    const long long timeout_cycles = (long long)x->timeout_ms * (clock_khz > 0 ? clock_khz : 2000000);
+    const uint32_t epoch = ++x->epoch;
+    const long long timeout_cycles = (long long)x->timeout_ms * x->clock_khz;
+    HashSink hs;
+    hs.lay = x->lay; hs.rank = r; hs.epoch = epoch; hs.done = x->d_done + 3;
+    for (int p = 0; p < P; p++) hs.window[p] = x->peer[p];
     { StageTimer tm(e, st, 7);
-    k_merge_blocks<<<(n_queries + kMergeWarps - 1) / kMergeWarps, kMergeWarps * 32, 0, st>>>(
-        x->window, x->world, x->max_q, sink.epoch, n_queries, max_rows, d_rows, d_n_rows, x->d_done + 1, timeout_cycles); }
+    int sms = 148;
+    k_publish_hashes<<<2 * sms, 256, 0, st>>>(fp.d_hash, fp.d_t_anchor, fp.d_hash_off, fp.d_status, hi - lo, lo, hs);
+    k_wait_hashes<<<1, 32, 0, st>>>(x->window, P, epoch, x->d_done + 1, timeout_cycles); }
     AID_CUDA(e, cudaGetLastError());
-    e->launches += 1;
-    return AID_OK;
+    e->launches += 2;
+    const int parity = (int)(epoch & 1u);
+    const uint32_t* wh = x->lay.hash(x->window, parity);
+    return match_and_merge(e, x, epoch, wh, x->lay.t(x->window, parity), x->lay.begins(x->window, parity),
+                           x->lay.lens(x->window, parity), nullptr, n_windows, d_track_map, n_map, d_rows, max_rows,
+                           d_n_rows, st);
 }

@@ -41,35 +41,60 @@ struct Index {
     DevBuf cand, cand_n, rows, rows_n;
 };
 
-// ---- sharded identification: where k_rank delivers a window's rows (exchange.cu) -------------------------------
-// With world == 0 the rows go to the caller's buffers. Otherwise every rank owns a receive window (one device
-// allocation, mapped into its peers through CUDA IPC or used directly inside one process):
-//   flags  u32[AID_MAX_RANKS]                          epoch of the last complete block received from rank r
-//   counts i32[2][world][max_q]                        rows per window        (double-buffered by epoch parity)
-//   rows   aid_match_row[2][world][max_q][AID_MAX_ROWS]
-// and k_rank stores each window's rows, already in global track numbers, into slot [epoch & 1][rank] of EVERY window
-// over NVLink; the last CTA to finish publishes the epoch in every window's flag. The merge kernel of the receiving
-// rank waits for the world's flags and merges the blocks. No NCCL call, no host round trip.
+// ---- sharded identification over peer memory (exchange.cu) ---------------------------------------------------
+// Every rank owns a receive window (one device allocation, mapped into its peers through CUDA IPC or used directly
+// inside one process). Everything that changes per call is double-buffered by epoch parity:
+//   flag page (256 B)  u32 row_flag[8] | u32 hash_flag[8] (at +64) | u32 hash_status[8] (at +128):
+//                      epoch of the last complete row block / hash block received from rank r
+//   counts  i32[2][world][max_q]                        rows per window and source rank
+//   rows    aid_match_row[2][world][max_q][AID_MAX_ROWS]
+//   begins  u32[2][max_q], lens u32[2][max_q]           where window q's hashes sit in `hash`/`t` (whole batch)
+//   hash    u32[2][world][hcap], t u32[2][world][hcap]  the query fingerprints rank r computed for its slice of the batch
+// k_publish_hashes stores a rank's fingerprints into every window, k_rank (match.cu) stores each window's rows,
+// already in global track numbers, into slot [epoch & 1][rank] of every window; in both the last CTA to finish
+// publishes the epoch in every window's flag, and the consumer kernel of the receiving rank waits for the world's
+// flags on the device. No NCCL call, no host round trip. With world == 0 a RowSink means "rows go to the caller".
 constexpr size_t kXchgFlagBytes = 256;
+struct XchgLayout {
+    int world = 0, max_q = 0;
+    uint32_t hcap = 0;
+    size_t off_counts = 0, off_rows = 0, off_begins = 0, off_lens = 0, off_hash = 0, off_t = 0, bytes = 0;
+    static XchgLayout make(int world, int max_q, uint32_t hcap) {
+        XchgLayout L; L.world = world; L.max_q = max_q; L.hcap = hcap;
+        auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+        size_t o = kXchgFlagBytes;
+        L.off_counts = o; o = up(o + (size_t)2 * world * max_q * 4);
+        L.off_rows = o;   o = up(o + (size_t)2 * world * max_q * AID_MAX_ROWS * sizeof(aid_match_row));
+        L.off_begins = o; o = up(o + (size_t)2 * max_q * 4);
+        L.off_lens = o;   o = up(o + (size_t)2 * max_q * 4);
+        L.off_hash = o;   o = up(o + (size_t)2 * world * hcap * 4);
+        L.off_t = o;      o = up(o + (size_t)2 * world * hcap * 4);
+        L.bytes = o;
+        return L;
+    }
+    __host__ __device__ int32_t* counts(unsigned char* w, int parity, int src) const {
+        return reinterpret_cast<int32_t*>(w + off_counts) + ((size_t)parity * world + src) * max_q;
+    }
+    __host__ __device__ aid_match_row* rows(unsigned char* w, int parity, int src) const {
+        return reinterpret_cast<aid_match_row*>(w + off_rows) + ((size_t)parity * world + src) * max_q * AID_MAX_ROWS;
+    }
+    __host__ __device__ uint32_t* begins(unsigned char* w, int parity) const { return reinterpret_cast<uint32_t*>(w + off_begins) + (size_t)parity * max_q; }
+    __host__ __device__ uint32_t* lens(unsigned char* w, int parity) const { return reinterpret_cast<uint32_t*>(w + off_lens) + (size_t)parity * max_q; }
+    __host__ __device__ uint32_t* hash(unsigned char* w, int parity) const { return reinterpret_cast<uint32_t*>(w + off_hash) + (size_t)parity * world * hcap; }
+    __host__ __device__ uint32_t* t(unsigned char* w, int parity) const { return reinterpret_cast<uint32_t*>(w + off_t) + (size_t)parity * world * hcap; }
+    __host__ __device__ static uint32_t* row_flag(unsigned char* w) { return reinterpret_cast<uint32_t*>(w); }
+    __host__ __device__ static uint32_t* hash_flag(unsigned char* w) { return reinterpret_cast<uint32_t*>(w) + 16; }
+    __host__ __device__ static uint32_t* hash_status(unsigned char* w) { return reinterpret_cast<uint32_t*>(w) + 32; }
+};
 struct RowSink {
-    int world = 0, rank = 0, max_q = 0;
+    XchgLayout lay;                             // lay.world == 0: rows go to the caller's buffers
+    int rank = 0;
     uint32_t epoch = 0;
-    unsigned char* window[AID_MAX_RANKS] = {};   // peers' receive windows (window[rank] is this rank's own)
+    unsigned char* window[AID_MAX_RANKS] = {};   // the ranks' receive windows (window[rank] is this rank's own)
     uint32_t* done = nullptr;                   // CTA completion counter (local)
     const uint32_t* track_map = nullptr;        // engine track number -> global track number (or null)
     uint32_t n_map = 0;
 };
-__host__ __device__ inline int32_t* xchg_counts(unsigned char* w, int world, int max_q, int parity, int src) {
-    return reinterpret_cast<int32_t*>(w + kXchgFlagBytes) + ((size_t)parity * world + src) * max_q;
-}
-__host__ __device__ inline aid_match_row* xchg_rows(unsigned char* w, int world, int max_q, int parity, int src) {
-    const size_t counts_bytes = ((size_t)2 * world * max_q * 4 + 255) / 256 * 256;
-    return reinterpret_cast<aid_match_row*>(w + kXchgFlagBytes + counts_bytes) + ((size_t)parity * world + src) * max_q * AID_MAX_ROWS;
-}
-inline size_t xchg_window_bytes(int world, int max_q) {
-    const size_t counts_bytes = ((size_t)2 * world * max_q * 4 + 255) / 256 * 256;
-    return kXchgFlagBytes + counts_bytes + (size_t)2 * world * max_q * AID_MAX_ROWS * sizeof(aid_match_row);
-}
 // match.cu: probe + vote + rank for n_q windows; rows go to (d_rows, d_n_rows) or, with sink.world > 0, to the peers
 int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
                          const uint32_t* d_hash_len, const int32_t* d_status, int n_q, aid_match_row* d_rows,

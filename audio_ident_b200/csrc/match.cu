@@ -305,7 +305,7 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
         r.q_first = (int32_t)(c.tq & 0xffffu);
         r.q_last = (int32_t)(c.tq >> 16);
     }
-    if (sink.world == 0) {
+    if (sink.lay.world == 0) {
         if (tid < (int)n) rows[(int64_t)q * max_rows + tid] = r;
         if (tid == 0) n_rows[q] = (int32_t)n;
         return;
@@ -314,10 +314,10 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
     // The order inside a rank's block is by local track number; the receiver orders the union by global number.
     if (tid < (int)n && sink.track_map) r.track = r.track < sink.n_map ? sink.track_map[r.track] : 0xffffffffu;
     const int parity = (int)(sink.epoch & 1u);
-    for (int p = 0; p < sink.world; p++) {
+    for (int p = 0; p < sink.lay.world; p++) {
         unsigned char* w = sink.window[p];
-        if (tid < (int)n) xchg_rows(w, sink.world, sink.max_q, parity, sink.rank)[(int64_t)q * AID_MAX_ROWS + tid] = r;
-        if (tid == 0) xchg_counts(w, sink.world, sink.max_q, parity, sink.rank)[q] = (int32_t)n;
+        if (tid < (int)n) sink.lay.rows(w, parity, sink.rank)[(int64_t)q * AID_MAX_ROWS + tid] = r;
+        if (tid == 0) sink.lay.counts(w, parity, sink.rank)[q] = (int32_t)n;
     }
     __threadfence_system();                       // this thread's peer stores are visible system-wide ...
     __syncthreads();
@@ -326,8 +326,8 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
         if (prev == gridDim.x - 1) {              // ... so when the last CTA gets here, the whole block is
             *sink.done = 0;
             __threadfence_system();
-            for (int p = 0; p < sink.world; p++) {
-                uint32_t* flag = reinterpret_cast<uint32_t*>(sink.window[p]) + sink.rank;
+            for (int p = 0; p < sink.lay.world; p++) {
+                uint32_t* flag = XchgLayout::row_flag(sink.window[p]) + sink.rank;
                 asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(sink.epoch) : "memory");
             }
         }
@@ -348,7 +348,7 @@ int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* 
     const int n_seg = (int)ix->segs.size();
     if (n_q == 0) return AID_OK;
     if (n_seg == 0) {
-        if (sink.world == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
+        if (sink.lay.world == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
         // an empty shard still has to publish its (empty) block: the peers wait for it
         k_rank<<<n_q, kThreads, 0, st>>>(nullptr, nullptr, nullptr, 0, max_rows, nullptr, nullptr, sink);
         AID_CUDA(e, cudaGetLastError());

@@ -289,9 +289,9 @@ class Engine:
                                           _ptr(d_status), int(n_queries), _ptr(d_rows), int(max_rows), _ptr(d_n_rows),
                                           _ptr(stream)))
 
-    def exchange(self, rank: int, world: int, max_queries: int) -> "Exchange":
+    def exchange(self, rank: int, world: int, max_queries: int, max_hashes_per_rank: int = 0) -> "Exchange":
         """This rank's receive window for sharded identification (aid_exchange_create)."""
-        x = Exchange(self, rank, world, max_queries)
+        x = Exchange(self, rank, world, max_queries, max_hashes_per_rank)
         self.__dict__.setdefault("_exchanges", []).append(x)
         return x
 
@@ -302,6 +302,15 @@ class Engine:
         self._check(self._L.aid_match_exchange_dev(self._h, xchg._h, _ptr(d_hash), _ptr(d_t), _ptr(d_hash_off),
                                                    _ptr(d_hash_len), _ptr(d_status), int(n_queries), _ptr(d_track_map),
                                                    int(n_map), _ptr(d_rows), int(max_rows), _ptr(d_n_rows), _ptr(stream)))
+
+    def identify_exchange_dev(self, xchg: "Exchange", d_pcm, sample_off, d_track_map, n_map: int, d_rows, d_n_rows,
+                              max_rows: int = MAX_ROWS, stream=None) -> None:
+        """The whole sharded identification step on the device (aid_identify_exchange_dev): this rank fingerprints
+        its slice of the window batch, fingerprints and rows travel through the ranks' windows over NVLink."""
+        sample_off, offp = self._off(sample_off)
+        self._check(self._L.aid_identify_exchange_dev(self._h, xchg._h, _ptr(d_pcm), offp, len(sample_off) - 1,
+                                                      _ptr(d_track_map), int(n_map), _ptr(d_rows), int(max_rows),
+                                                      _ptr(d_n_rows), _ptr(stream)))
 
     def copy_device(self, d_dst, d_src, nbytes: int, stream=None) -> None:
         self._check(self._L.aid_copy_device(self._h, _ptr(d_dst), _ptr(d_src), int(nbytes), _ptr(stream)))
@@ -335,10 +344,11 @@ class Exchange:
 
     HANDLE_BYTES = 64
 
-    def __init__(self, engine: Engine, rank: int, world: int, max_queries: int):
+    def __init__(self, engine: Engine, rank: int, world: int, max_queries: int, max_hashes_per_rank: int = 0):
         self.engine, self.rank, self.world, self.max_queries = engine, int(rank), int(world), int(max_queries)
         h = C.c_void_p()
-        engine._check(engine._L.aid_exchange_create(engine._h, self.rank, self.world, self.max_queries, C.byref(h)))
+        engine._check(engine._L.aid_exchange_create(engine._h, self.rank, self.world, self.max_queries,
+                                                    int(max_hashes_per_rank), C.byref(h)))
         self._h = h
 
     def handle(self) -> bytes:

@@ -161,8 +161,29 @@ class ShardedIdentifier:
             return merge_rows(blk[None])
         return merge_rows(self._all_gather(blk))
 
+    def _query_fused(self, d_pcm, sample_off):
+        """Whole identification step as one engine call (aid_identify_exchange_dev): split fingerprinting, fingerprints
+        and rows exchanged through the ranks' windows over NVLink, merge on the device. No NCCL call, no host
+        synchronisation; the only torch work is shaping the result."""
+        import torch
+        n = len(sample_off) - 1
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=self.device)
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._stream):
+            i32 = dict(dtype=torch.int32, device=self.device)
+            if self._map_dev is None:
+                self._map_dev = torch.tensor(self.to_global if self.to_global else [0], **i32)
+            rows = torch.empty((n, MAX_ROWS, 5), **i32)
+            nrows = torch.empty(n, **i32)
+            self.backend.identify_exchange_dev(self._xchg, d_pcm, sample_off, self._map_dev, len(self.to_global), rows,
+                                               nrows, MAX_ROWS, self._stream.cuda_stream)
+            out = self._rows_out(rows, nrows)
+        torch.cuda.current_stream(self.device).wait_stream(self._stream)
+        return out
+
     def _query_device(self, d_pcm, sample_off):
-        """Whole identification step without host round trips: split fingerprinting, NCCL all-gather of the hashes
+        """The same step with NCCL (kept for comparison and for batches larger than the exchange was sized for): split fingerprinting, NCCL all-gather of the hashes
         (padded to the largest rank), local probe/vote on device buffers, all-gather of the row blocks, merge.
         One host synchronisation (the per-rank hash totals, needed to size the exchange buffer)."""
         import torch
@@ -229,6 +250,8 @@ class ShardedIdentifier:
         sample_off = np.ascontiguousarray(sample_off, np.int64)
         n = len(sample_off) - 1
         if device and self.device is not None and split_fingerprint and n >= self.world and hasattr(self.backend, "match_dev"):
+            if self._xchg is not None and n <= self._xchg.max_queries:
+                return self._query_fused(pcm, sample_off)
             return self._query_device(pcm, sample_off)
         if self.world == 1 or not split_fingerprint or n < self.world:
             rows, nr = self.backend.query(pcm, sample_off, device=device)

@@ -180,7 +180,10 @@ int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t_anc
 #define AID_MAX_RANKS 8
 #define AID_IPC_HANDLE_BYTES 64
 typedef struct aid_exchange aid_exchange;
-int  aid_exchange_create(aid_engine* e, int rank, int world, int max_queries, aid_exchange** out);
+/* max_queries: windows per call; max_hashes_per_rank: room for the query fingerprints one rank contributes per call
+ * (0 = 1024 per window of a rank's slice; a 3.5 s window yields about 300) */
+int  aid_exchange_create(aid_engine* e, int rank, int world, int max_queries, int64_t max_hashes_per_rank,
+                         aid_exchange** out);
 void aid_exchange_destroy(aid_exchange* x);
 /* handle[64] of this rank's window for ranks in other processes (a cudaIpcMemHandle_t) */
 int  aid_exchange_handle(aid_exchange* x, uint8_t* handle);
@@ -190,7 +193,8 @@ int  aid_exchange_connect(aid_exchange* x, const uint8_t* handles);
 int  aid_exchange_connect_local(aid_exchange* x, aid_exchange* const* peers);
 /* how long the merge kernel waits for the slowest rank before it gives up (default 20 s) */
 int  aid_exchange_set_timeout_ms(aid_exchange* x, int64_t ms);
-/* AID_OK, or AID_E_TIMEOUT if a merge gave up waiting (n_rows of its windows are -1); synchronises */
+/* AID_OK; AID_E_TIMEOUT if a kernel gave up waiting for a peer (n_rows of the affected windows are -1);
+ * AID_E_CAPACITY if a rank's fingerprints did not fit max_hashes_per_rank (its windows matched nothing). Synchronises. */
 int  aid_exchange_status(aid_exchange* x);
 /* aid_match_dev + exchange + merge. d_track_map[n_map] (device, may be NULL) maps this engine's track numbers to
  * global ones; d_rows[n_queries][max_rows] / d_n_rows[n_queries] receive the merged rows. Asynchronous on stream. */
@@ -198,6 +202,15 @@ int  aid_match_exchange_dev(aid_engine* e, aid_exchange* x, const uint32_t* d_ha
                             const uint32_t* d_hash_off, const uint32_t* d_hash_len, const int32_t* d_status,
                             int n_queries, const uint32_t* d_track_map, int64_t n_map, aid_match_row* d_rows,
                             int max_rows, int32_t* d_n_rows, void* stream);
+
+/* The whole sharded step with device-resident query PCM: the batch is sample_off[0..n_windows] (host, identical on
+ * every rank); rank r fingerprints windows [r*n/world, (r+1)*n/world), stores the fingerprints into every rank's
+ * window, waits on the device for the other slices, probes its shard for ALL windows, and exchanges + merges the rows
+ * as aid_match_exchange_dev does. Replaces two NCCL all-gathers, the host synchronisation that sized them and the
+ * torch merge of the earlier path. */
+int  aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const float* d_pcm, const int64_t* sample_off,
+                               int n_windows, const uint32_t* d_track_map, int64_t n_map, aid_match_row* d_rows,
+                               int max_rows, int32_t* d_n_rows, void* stream);
 
 /* ---- content-duplicate scan ----------------------------------------------
  * Replaces the per-row Python loop of audio-ident-service/app/audio/dedup.py:170-222 (check_content_duplicate)

@@ -138,6 +138,22 @@ def test_fused_rank_exchange_equals_one_index(engine):
                 for q in range(n):
                     assert np.array_equal(m[q, :nn[q]], single[q, :nn[q]]), (epoch, sh.rank, q)
             assert (n1[:18] >= 1).all() and n1[18] == 0
+            # the whole step as one engine call per rank (aid_identify_exchange_dev): each rank fingerprints a third of
+            # the windows, fingerprints and rows travel through the windows; callers sit on separate streams so that
+            # no rank's stream waits for another rank's on the host side
+            d_pcm = torch.from_numpy(qp).cuda()
+            fused = []
+            for (e, sh), st in zip(ranks, streams):
+                with torch.cuda.stream(st):
+                    fused.append(sh.query(d_pcm.data_ptr(), qo, device=True))
+            torch.cuda.synchronize()
+            for (e, sh), (merged, nn_) in zip(ranks, fused):
+                sh._xchg.check()
+                assert np.array_equal(nn_.cpu().numpy(), n1)
+                m = merged.cpu().numpy()
+                for q in range(n):
+                    assert np.array_equal(m[q, :n1[q]], single[q, :n1[q]]), (epoch, sh.rank, q, "fused step")
+                assert (m[np.arange(50)[None, :] >= n1[:, None]] == -1).all()
             if epoch == 0:                          # query 2 is the triplicated track: rows from all three ranks interleave
                 assert n1[6] >= 4 and {int(x) for x in single[6, :4, 1]} == {2, 9, 10, 11}
     finally:
