@@ -41,14 +41,17 @@ struct aid_peak_run {      // one warp of the peak kernel: `n_blocks` consecutiv
 // ---- kernel launchers (defined in the .cu files, called by engine.cu) --------------
 struct aid_tables {              // device-resident constant tables, built once per engine
     const float* window;         // [1024] float32 Hamming
-    const float* twist;          // [32 lanes k1][32] twiddles of the second STFT transform, see aid_fill_stft_tables
+    const float* twist;          // [AID_TWIST_FLOATS] twiddles between / inside the STFT transforms, see aid_fill_stft_tables
 };
+constexpr int AID_TWIST_FOLDED = 32 * 32;              // floats of the folded table
+constexpr int AID_TWIST_FLOATS = 32 * 32 + 32 * 64;    // + the plain table W_1024^(n1*k1)
 
 // Host-side definition of the two tables (double precision, rounded to float once).
 //  window[n] : symmetric Hamming, the formula of oracle/aid_oracle.c tables_init.
 //  twist[k1][2*i], [2*i+1] = (c, s) of the twiddle w = c - i s = g^m * W_(2h)^k with g = W_1024^k1, for
 //    i = 0: stage 0 (m 16, h 1, k 0)      i = 1: stage 1 (m 8, h 2, k 0)      i = 2..3: stage 2 (m 4, h 4, k 0..1)
 //    i = 4..7: stage 3 (m 2, h 8, k 0..3)  i = 8..15: stage 4 (m 1, h 16, k 0..7)
+//  twist[1024 + k1*64 + 2*n1], [+1] = (c, s) of W_1024^(n1*k1) = c - i s: the inter-transform twiddle itself.
 inline void aid_fill_stft_tables(float* window, float* twist) {
     const double two_pi = 6.283185307179586476925286766559;
     for (int i = 0; i < AID_NFFT; i++)
@@ -62,6 +65,11 @@ inline void aid_fill_stft_tables(float* window, float* twist) {
                 twist[k1 * 32 + 2 * i] = (float)cos(a);
                 twist[k1 * 32 + 2 * i + 1] = (float)sin(a);
             }
+        }
+        for (int n1 = 0; n1 < 32; n1++) {
+            const double a = two_pi * (double)(k1 * n1) / (double)AID_NFFT;
+            twist[AID_TWIST_FOLDED + k1 * 64 + 2 * n1] = (float)cos(a);
+            twist[AID_TWIST_FOLDED + k1 * 64 + 2 * n1 + 1] = (float)sin(a);
         }
     }
 }

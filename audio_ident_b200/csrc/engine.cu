@@ -79,7 +79,7 @@ extern "C" int aid_engine_create(int device, aid_engine** out) {
         if ((ce = cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming)) != cudaSuccess) return fail(ce, "cudaEventCreate");
     }
     // constant tables (definition: aid_fill_stft_tables in common.cuh)
-    std::vector<float> win(AID_NFFT), tw(32 * 32);
+    std::vector<float> win(AID_NFFT), tw(AID_TWIST_FLOATS);
     aid_fill_stft_tables(win.data(), tw.data());
     if ((ce = e->d_window.ensure(win.size() * sizeof(float))) != cudaSuccess) return fail(ce, "cudaMalloc(window)");
     if ((ce = e->d_twiddle.ensure(tw.size() * sizeof(float))) != cudaSuccess) return fail(ce, "cudaMalloc(twist)");

@@ -8,8 +8,9 @@
 //  * One warp owns a run of consecutive frames of one track. Two frames a, b = a+1 are packed into one
 //    1024-point COMPLEX transform z = a + i*b, factored 32 x 32: lane n1 holds z[n1 + 32*n2] for
 //    n2 = 0..31 in registers, does a 32-point FFT over n2 (its first stage fused with the window
-//    multiply), the warp transposes through its private shared-memory tile, lane k1 does the second
-//    32-point transform over n1 with the twiddles W_1024^(n1*k1) folded into its butterflies and ends up
+//    multiply), the warp transposes through its private shared-memory tile, lane k1 multiplies its row by
+//    the twiddles W_1024^(n1*k1) while gathering it, does the second 32-point transform over n1 (constant
+//    twiddles as immediates; AID_STFT_UNFOLD = 0 folds the twiddles into its butterflies instead) and ends up
 //    holding Z[k1 + 32*k2]. Z[N-k] lives in lane (32-k1)&31, so the two real spectra are separated with
 //    one shuffle per value.
 //  * Because the hop is 128 = 4*32 samples, lane n1 needs x[32*m + n1] for a window of m that slides by 4
@@ -73,6 +74,11 @@ __device__ __forceinline__ void stage(float (&re)[32], float (&im)[32]) {
         butterfly<g * 2 * half + k, g * 2 * half + k + half, k * (16 >> S)>(re, im);
         stage<S, I + 1>(re, im);
     }
+}
+
+// All five stages with constant twiddles (second transform of the AID_STFT_UNFOLD variant).
+__device__ __forceinline__ void fft32_const(float (&re)[32], float (&im)[32]) {
+    stage<0, 0>(re, im); stage<1, 0>(re, im); stage<2, 0>(re, im); stage<3, 0>(re, im); stage<4, 0>(re, im);
 }
 
 // Stages 1..4 of the DIT transform (stage 0 is fused with the window multiply, see k_stft).
@@ -147,6 +153,23 @@ __device__ __forceinline__ float log1p_power(float re, float im) {
 #ifndef AID_STFT_MIN_CTAS
 #define AID_STFT_MIN_CTAS 3
 #endif
+// Timing-only ablation switches for tools/microbench/stft_bench.cu (profiles/r01_stft_v3.md); 0 in the product build.
+// 1: one store per value pair instead of two  2: no logarithm  4: no mirror shuffles  8: no transpose through shared
+// memory  16: second transform skipped  32: first transform (stages 1-4) skipped. Results are wrong with any bit set.
+#ifndef AID_STFT_ABLATE
+#define AID_STFT_ABLATE 0
+#endif
+constexpr int kAblate = AID_STFT_ABLATE;
+// 1: the inter-transform twiddle W_1024^(n1*k1) is applied as 31 complex multiplies while the transposed row is
+//    gathered, and the second transform uses constant twiddles (FFMA with immediates: two register operands) instead
+//    of folding the twiddle into 80 general butterflies whose FFMAs read three registers.
+// 2: window products as FMUL + FADD/FADD instead of FMUL + two three-register FFMAs.
+// Measured (profiles/r01_stft_v3.md): 0 -> 53.4 %, 1 -> 54.6 %, 2 -> 52.6 %, 3 -> 53.8 % of the HBM roofline.
+#ifndef AID_STFT_UNFOLD
+#define AID_STFT_UNFOLD 1
+#endif
+constexpr int kUnfold = AID_STFT_UNFOLD;
+constexpr int kTwistStride = (kUnfold & 1) ? 68 : 36;  // floats per lane row of the twiddle table (16 B aligned, conflict-free LDS.128)
 constexpr int kTabStride = 36;                         // floats per lane row of the two lane-major tables (16 B aligned, conflict-free LDS.128)
 
 // 3 CTAs x 4 warps per SM: 142 registers, no spills. Measured alternatives (tools/microbench/stft_bench.cu, 2048 x 30 s
@@ -159,14 +182,16 @@ k_stft(const float* __restrict__ window, const float* __restrict__ twist,
        const float* __restrict__ pcm, const aid_stft_unit* __restrict__ units, int n_units,
        float* __restrict__ spec) {
     __shared__ __align__(16) float s_win[32 * kTabStride];       // [lane][j]  = window[lane + 32 j]
-    __shared__ __align__(16) float s_twist[32 * kTabStride];     // [lane][..] = AID_TWIST layout (engine.cu)
+    __shared__ __align__(16) float s_twist[32 * kTwistStride];   // [lane][..] = one of the two AID_TWIST layouts (common.cuh)
     __shared__ __align__(16) float2 s_tile[kWarpsPerCta][kTileFloats];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
         s_win[(i & 31) * kTabStride + (i >> 5)] = 0.5f * window[i];      // exact halving: Z = X_a + i X_b after the mirror sums below
-        s_twist[(i >> 5) * kTabStride + (i & 31)] = twist[i];
+        if constexpr (!(kUnfold & 1)) s_twist[(i >> 5) * kTwistStride + (i & 31)] = twist[i];
     }
+    if constexpr (kUnfold & 1)
+        for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) s_twist[(i >> 6) * kTwistStride + (i & 63)] = twist[AID_TWIST_FOLDED + i];
     __syncthreads();
 
     const int unit_id = blockIdx.x * kWarpsPerCta + warp;
@@ -185,7 +210,7 @@ k_stft(const float* __restrict__ window, const float* __restrict__ twist,
     float2* tile = s_tile[warp];
     const float4* tile_row = reinterpret_cast<const float4*>(tile + lane * kTileStride);
     const float4* win4 = reinterpret_cast<const float4*>(s_win + lane * kTabStride);
-    const float4* twist4 = reinterpret_cast<const float4*>(s_twist + lane * kTabStride);
+    const float4* twist4 = reinterpret_cast<const float4*>(s_twist + lane * kTwistStride);
     const int partner = (32 - lane) & 31;
     float* row_a = spec + u.spec_row * AID_NBINS + lane;
 
@@ -206,39 +231,67 @@ k_stft(const float* __restrict__ window, const float* __restrict__ twist,
             for (int r = 0; r < 4; r++) {
                 const int ja = 4 * q + r, jb = ja + 16, e = bitrev5(ja);
                 const float tr = wb[r] * ring[jb], ti = wb[r] * ring[jb + 4];
-                re[e] = fmaf(wa[r], ring[ja], tr);     re[e + 1] = fmaf(wa[r], ring[ja], -tr);
-                im[e] = fmaf(wa[r], ring[ja + 4], ti); im[e + 1] = fmaf(wa[r], ring[ja + 4], -ti);
+                if constexpr (kUnfold & 2) {
+                    const float ur = __fmul_rn(wa[r], ring[ja]), ui = __fmul_rn(wa[r], ring[ja + 4]);   // no contraction
+                    re[e] = __fadd_rn(ur, tr); re[e + 1] = __fsub_rn(ur, tr);
+                    im[e] = __fadd_rn(ui, ti); im[e + 1] = __fsub_rn(ui, ti);
+                } else {
+                    re[e] = fmaf(wa[r], ring[ja], tr);     re[e + 1] = fmaf(wa[r], ring[ja], -tr);
+                    im[e] = fmaf(wa[r], ring[ja + 4], ti); im[e + 1] = fmaf(wa[r], ring[ja + 4], -ti);
+                }
             }
         }
-        fft32_after_stage0(re, im);                      // over n2: Y[k1] in element k1
+        if constexpr (!(kAblate & 32)) fft32_after_stage0(re, im);   // over n2: Y[k1] in element k1
 
         // transpose: lane n1 scatters Y[k1] to tile[k1][n1]; lane k1 gathers its row two values at a time
+        if constexpr (!(kAblate & 8)) {
 #pragma unroll
-        for (int k1 = 0; k1 < 32; k1++) tile[k1 * kTileStride + lane] = make_float2(re[k1], im[k1]);
-        __syncwarp();
+            for (int k1 = 0; k1 < 32; k1++) tile[k1 * kTileStride + lane] = make_float2(re[k1], im[k1]);
+            __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const float4 z = tile_row[q];
-            re[bitrev5(2 * q)] = z.x;     im[bitrev5(2 * q)] = z.y;
-            re[bitrev5(2 * q + 1)] = z.z; im[bitrev5(2 * q + 1)] = z.w;
+            for (int q = 0; q < 16; q++) {
+                const float4 z = tile_row[q];
+                if constexpr (kUnfold & 1) {                 // y[n1] * W_1024^(n1*k1), w = c - i s
+                    const float4 w = twist4[q];
+                    if (q == 0) { re[0] = z.x; im[0] = z.y; }
+                    else {
+                        re[bitrev5(2 * q)] = fmaf(z.x, w.x, z.y * w.y);
+                        im[bitrev5(2 * q)] = fmaf(z.y, w.x, -(z.x * w.y));
+                    }
+                    re[bitrev5(2 * q + 1)] = fmaf(z.z, w.z, z.w * w.w);
+                    im[bitrev5(2 * q + 1)] = fmaf(z.w, w.z, -(z.z * w.w));
+                } else {
+                    re[bitrev5(2 * q)] = z.x;     im[bitrev5(2 * q)] = z.y;
+                    re[bitrev5(2 * q + 1)] = z.z; im[bitrev5(2 * q + 1)] = z.w;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
 
-        fft32_twisted(re, im, twist4);                   // over n1: Z[lane + 32*k2] in element k2
+        if constexpr (!(kAblate & 16)) {                     // over n1: Z[lane + 32*k2] in element k2
+            if constexpr (kUnfold & 1) fft32_const(re, im); else fft32_twisted(re, im, twist4);
+        }
 
         const bool has_b = p + 1 < u.n_frames;
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) {
             const float zr = re[k2], zi = im[k2];
             // mirror Z[1024 - k]: lane (32-k1)&31, k2' = 31 - k2 (k1 != 0) or (32 - k2)&31 (k1 == 0)
-            const float sr = __shfl_sync(AID_FULL_MASK, re[31 - k2], partner);
-            const float si = __shfl_sync(AID_FULL_MASK, im[31 - k2], partner);
+            const float sr = (kAblate & 4) ? re[31 - k2] : __shfl_sync(AID_FULL_MASK, re[31 - k2], partner);
+            const float si = (kAblate & 4) ? im[31 - k2] : __shfl_sync(AID_FULL_MASK, im[31 - k2], partner);
             const float mr = lane == 0 ? re[(32 - k2) & 31] : sr;
             const float mi = lane == 0 ? im[(32 - k2) & 31] : si;
             const float ar = zr + mr, ai = zi - mi;      // X_a[k]   (the window table is pre-scaled by 1/2)
             const float br = zr - mr, bi = zi + mi;      // i * X_b[k]
-            row_a[32 * k2] = log1p_power(ar, ai);
-            if (has_b) row_a[AID_NBINS + 32 * k2] = log1p_power(br, bi);
+            if constexpr (kAblate & 2) {
+                row_a[32 * k2] = fmaf(ar, ar, ai * ai);
+                if (has_b) row_a[AID_NBINS + 32 * k2] = fmaf(br, br, bi * bi);
+            } else if constexpr (kAblate & 1) {
+                row_a[32 * k2] = log1p_power(ar, ai) + log1p_power(br, bi);
+            } else {
+                row_a[32 * k2] = log1p_power(ar, ai);
+                if (has_b) row_a[AID_NBINS + 32 * k2] = log1p_power(br, bi);
+            }
         }
         row_a += 2 * AID_NBINS;
 

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--snr-db", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ingest-chunk", type=int, default=512)
+    ap.add_argument("--also-queries", default="", help="comma-separated further batch sizes measured on the same index")
     ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer",
                     help="peer: k_rank stores rows into every rank's window over NVLink + device merge (aid_match_exchange_dev); "
                          "nccl: all-gather of 50-row blocks + torch sort (the earlier path, kept for comparison)")
@@ -95,96 +96,115 @@ def main():
     del buf
 
     # ---- queries (identical on every rank: same seed)
-    rng = np.random.default_rng(args.seed + 10**6)
-    q_track = rng.integers(0, args.tracks, args.queries)
-    q_start = rng.integers(0, samples - 80000 + 1, args.queries)
-    src = torch.empty(args.queries * samples, dtype=torch.float32, device=dev)
-    for j, g in enumerate(q_track):
-        eng.synth_tracks(src.data_ptr() + j * samples * 4, int(g), 1, samples, args.seed)
-    eng.sync()
-    idx = torch.from_numpy(q_start).to(dev)[:, None] + torch.arange(80000, device=dev)[None, :]
-    clips = src.view(args.queries, samples).gather(1, idx)
-    del src, idx
-    gen = torch.Generator(device=dev); gen.manual_seed(args.seed + 7)
-    p_sig = clips.pow(2).mean(dim=1, keepdim=True)
-    noise = torch.randn(clips.shape, generator=gen, device=dev) * torch.sqrt(p_sig / (10 ** (args.snr_db / 10)))
-    clips = (clips + noise).clamp_(-1.0, 1.0)
-    del noise
-    wins = torch.stack([clips[:, a:b] for a, b in WINDOWS], dim=1).contiguous()      # [Q, 3, 56000]
-    n_win = args.queries * 3
-    off = np.arange(n_win + 1, dtype=np.int64) * 56000
-    torch.cuda.synchronize()
+    def make_queries(n_queries: int, salt: int):
+        """n_queries noisy 5 s excerpts -> (windows tensor [Q, 3, 56000] on the device, true track, true start sample)"""
+        rng = np.random.default_rng(args.seed + 10**6 + salt)
+        q_track = rng.integers(0, args.tracks, n_queries)
+        q_start = rng.integers(0, samples - 80000 + 1, n_queries)
+        gen = torch.Generator(device=dev); gen.manual_seed(args.seed + 7 + salt)
+        wins = torch.empty((n_queries, 3, 56000), dtype=torch.float32, device=dev)
+        for c0 in range(0, n_queries, 2048):                        # bounded scratch: 2048 whole tracks at a time
+            c1 = min(c0 + 2048, n_queries)
+            src = torch.empty((c1 - c0) * samples, dtype=torch.float32, device=dev)
+            for j in range(c0, c1):
+                eng.synth_tracks(src.data_ptr() + (j - c0) * samples * 4, int(q_track[j]), 1, samples, args.seed)
+            eng.sync()
+            idx = torch.from_numpy(q_start[c0:c1]).to(dev)[:, None] + torch.arange(80000, device=dev)[None, :]
+            clips = src.view(c1 - c0, samples).gather(1, idx)
+            del src, idx
+            p_sig = clips.pow(2).mean(dim=1, keepdim=True)
+            noise = torch.randn(clips.shape, generator=gen, device=dev) * torch.sqrt(p_sig / (10 ** (args.snr_db / 10)))
+            clips = (clips + noise).clamp_(-1.0, 1.0)
+            del noise
+            for w, (a_, b_) in enumerate(WINDOWS):
+                wins[c0:c1, w] = clips[:, a_:b_]
+            del clips
+        torch.cuda.synchronize()
+        return wins, q_track, q_start
 
+    def measure(n_queries: int, salt: int):
+        wins, q_track, q_start = make_queries(n_queries, salt)
+        n_win = n_queries * 3
+        off = np.arange(n_win + 1, dtype=np.int64) * 56000
+
+        def step():
+            return sh.query(wins.data_ptr(), off, device=True)
+
+        for _ in range(args.warmup):
+            merged, n = step()
+        barrier()
+        eng.stage_times(); eng.set_stage_timing(True)
+        launches0 = eng.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()                                   # the step's own stream waits for / is waited on by this one
+        for _ in range(args.steps):
+            merged, n = step()
+        ev1.record()
+        torch.cuda.synchronize()
+        dt_wall = time.perf_counter() - t0
+        dt_dev = ev0.elapsed_time(ev1) * 1e-3
+        if sh._xchg is not None:
+            sh._xchg.check()
+        stage = eng.stage_times(); eng.set_stage_timing(False)
+        launches = eng.launches - launches0
+        t_all = torch.tensor([dt_dev, dt_wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dt = float(t_all[0].item()) / args.steps        # CUDA events on the launching stream, max over ranks
+        dt_wall = float(t_all[1].item()) / args.steps
+
+        # accuracy in the reference's terms: sum aligned hashes per track over the three windows, top-1
+        m = merged.cpu().numpy() if hasattr(merged, "cpu") else merged
+        top1 = 0
+        offs_ok = 0
+        for q in range(n_queries):
+            votes = {}
+            first_off = {}
+            for w in range(3):
+                r = m[3 * q + w]
+                r = r[r[:, 0] >= 0]
+                for cnt, tr, of in zip(r[:, 0], r[:, 1], r[:, 2]):
+                    votes[int(tr)] = votes.get(int(tr), 0) + int(cnt)
+                    first_off.setdefault((int(tr), w), int(of))
+            if votes:
+                best = max(votes, key=lambda k: (votes[k], -k))
+                if best == int(q_track[q]) and votes[best] >= 8:
+                    top1 += 1
+                    of0 = first_off.get((best, 0))
+                    offs_ok += of0 is not None and abs(of0 - q_start[q] / 128.0) <= 1.0
+        digest = int(np.bitwise_xor.reduce((m.astype(np.int64) * np.arange(1, 6)).sum(axis=2).reshape(-1) & 0xFFFFFFFF))
+        per_step = {k: v[0] / args.steps for k, v in stage.items()}
+        del wins
+        return {"queries": n_queries, "windows_per_step": n_win, "queries_per_s": n_queries / dt, "ms_per_step": dt * 1e3,
+                "ms_per_step_wall": dt_wall * 1e3, "top1_accuracy": top1 / n_queries,
+                "top1_offset_within_1_frame": offs_ok / max(top1, 1), "rows_digest": digest,
+                "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items()}, "gpu_launches": int(launches)}
+
+    sizes = [args.queries] + [int(x) for x in args.also_queries.split(",") if x.strip()]
     if args.exchange == "peer":
-        sh.enable_peer_exchange(n_win)
-
-    def step():
-        return sh.query(wins.data_ptr(), off, device=True)
-
-    for _ in range(args.warmup):
-        merged, n = step()
-    barrier()
-    eng.stage_times(); eng.set_stage_timing(True)
-    launches0 = eng.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ev0.record()                                   # the step's own stream waits for / is waited on by this one
-    for _ in range(args.steps):
-        merged, n = step()
-    ev1.record()
-    torch.cuda.synchronize()
-    dt_wall = time.perf_counter() - t0
-    dt_dev = ev0.elapsed_time(ev1) * 1e-3
-    if sh._xchg is not None:
-        sh._xchg.check()
-    stage = eng.stage_times(); eng.set_stage_timing(False)
-    launches = eng.launches - launches0
-    t_all = torch.tensor([dt_dev, dt_wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    dt = float(t_all[0].item()) / args.steps        # CUDA events on the launching stream, max over ranks
-    dt_wall = float(t_all[1].item()) / args.steps
-    qps = args.queries / dt
-
-    # ---- accuracy in the reference's terms: sum aligned hashes per track over the three windows, top-1
-    m = merged.cpu().numpy() if hasattr(merged, "cpu") else merged
-    top1 = 0
-    offs_ok = 0
-    for q in range(args.queries):
-        votes = {}
-        first_off = {}
-        for w in range(3):
-            r = m[3 * q + w]
-            r = r[r[:, 0] >= 0]
-            for cnt, tr, of in zip(r[:, 0], r[:, 1], r[:, 2]):
-                votes[int(tr)] = votes.get(int(tr), 0) + int(cnt)
-                first_off.setdefault((int(tr), w), int(of))
-        if votes:
-            best = max(votes, key=lambda k: (votes[k], -k))
-            if best == int(q_track[q]) and votes[best] >= 8:
-                top1 += 1
-                of0 = first_off.get((best, 0))
-                offs_ok += of0 is not None and abs(of0 - q_start[q] / 128.0) <= 1.0
-    digest = int(np.bitwise_xor.reduce((m.astype(np.int64) * np.arange(1, 6)).sum(axis=2).reshape(-1) & 0xFFFFFFFF))
+        sh.enable_peer_exchange(3 * max(sizes))
+    results = [measure(nq, salt) for salt, nq in enumerate(sizes)]
+    main_r = results[0]
 
     if rank == 0:
-        per_step = {k: (v[0] / args.steps, v[1] // max(args.steps, 1)) for k, v in stage.items()}
         print(json.dumps({
-            "metric": f"queries/sec vs {args.tracks}-track index", "value": qps, "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "metric": f"queries/sec vs {args.tracks}-track index", "value": main_r["queries_per_s"], "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"identify {args.queries} x 5 s queries (3 x 3.5 s windows, {args.snr_db:g} dB SNR) "
                                    f"against {args.tracks} x {args.seconds:g} s tracks", "index_sharding": f"track g on rank g % {world}",
-                       "windows_per_step": n_win},
-            "timed_region": "device-resident query PCM -> fingerprint -> hash all-gather -> probe/vote/rank -> row exchange -> "
+                       "windows_per_step": main_r["windows_per_step"]},
+            "timed_region": "device-resident query PCM -> fingerprint -> fingerprint exchange -> probe/vote/rank -> row exchange -> "
                             "merged rows on every rank (CUDA events, max over ranks; wall clock beside it)",
-            "exchange": args.exchange, "ms_per_step_wall": dt_wall * 1e3,
-            "top1_accuracy": top1 / args.queries, "top1_offset_within_1_frame": offs_ok / max(top1, 1),
-            "rows_digest": digest, "index": {"tracks_per_rank": stats["tracks"], "postings_per_rank": stats["postings"],
-                                             "segments_per_rank": stats["segments"], "device_bytes_per_rank": stats["device_bytes"],
-                                             "build_seconds": t_build},
-            "stage_ms_per_step": {k: round(v[0], 3) for k, v in per_step.items()},
-            "gpu_launches": int(launches),
+            "exchange": args.exchange, "ms_per_step_wall": main_r["ms_per_step_wall"],
+            "top1_accuracy": main_r["top1_accuracy"], "top1_offset_within_1_frame": main_r["top1_offset_within_1_frame"],
+            "rows_digest": main_r["rows_digest"],
+            "index": {"tracks_per_rank": stats["tracks"], "postings_per_rank": stats["postings"],
+                      "segments_per_rank": stats["segments"], "device_bytes_per_rank": stats["device_bytes"],
+                      "build_seconds": t_build},
+            "stage_ms_per_step": main_r["stage_ms_per_step"], "gpu_launches": main_r["gpu_launches"],
+            "other_batch_sizes": results[1:],
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -36,10 +36,10 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_pcm, tracks * ns * 4)); CK(cudaMalloc(&d_spec, tracks * T * AID_NBINS * 4));
     CK(cudaMalloc(&d_units, units.size() * sizeof(aid_stft_unit)));
     CK(cudaMemcpy(d_units, units.data(), units.size() * sizeof(aid_stft_unit), cudaMemcpyHostToDevice));
-    std::vector<float> win(AID_NFFT), tw(32 * 32);
+    std::vector<float> win(AID_NFFT), tw(AID_TWIST_FLOATS);
     aid_fill_stft_tables(win.data(), tw.data());
-    CK(cudaMalloc(&d_win, 4096)); CK(cudaMalloc(&d_tw, 4096));
-    CK(cudaMemcpy(d_win, win.data(), 4096, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_tw, tw.data(), 4096, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_win, 4096)); CK(cudaMalloc(&d_tw, tw.size() * 4));
+    CK(cudaMemcpy(d_win, win.data(), 4096, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_tw, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     k_fill<<<148 * 8, 256>>>(d_pcm, tracks * ns, 12345u);
     CK(cudaDeviceSynchronize());
     aid_tables tb{d_win, d_tw};
