@@ -8,9 +8,9 @@
 //  * One warp owns a run of consecutive frames of one track. Two frames a, b = a+1 are packed into one
 //    1024-point COMPLEX transform z = a + i*b, factored 32 x 32: lane n1 holds z[n1 + 32*n2] for
 //    n2 = 0..31 in registers, does a 32-point FFT over n2 (its first stage fused with the window
-//    multiply), the warp transposes through its private shared-memory tile, lane k1 multiplies its row by
-//    the twiddles W_1024^(n1*k1) while gathering it, does the second 32-point transform over n1 (constant
-//    twiddles as immediates; AID_STFT_UNFOLD = 0 folds the twiddles into its butterflies instead) and ends up
+//    multiply), the warp transposes through its private shared-memory tile, lane k1 does the second
+//    32-point transform over n1 with the twiddles W_1024^(n1*k1) folded into its butterflies (AID_STFT_UNFOLD = 1:
+//    31 complex multiplies while gathering the row, then constant twiddles as immediates) and ends up
 //    holding Z[k1 + 32*k2]. Z[N-k] lives in lane (32-k1)&31, so the two real spectra are separated with
 //    one shuffle per value.
 //  * Because the hop is 128 = 4*32 samples, lane n1 needs x[32*m + n1] for a window of m that slides by 4
@@ -164,9 +164,11 @@ constexpr int kAblate = AID_STFT_ABLATE;
 //    gathered, and the second transform uses constant twiddles (FFMA with immediates: two register operands) instead
 //    of folding the twiddle into 80 general butterflies whose FFMAs read three registers.
 // 2: window products as FMUL + FADD/FADD instead of FMUL + two three-register FFMAs.
-// Measured (profiles/r01_stft_v3.md): 0 -> 53.4 %, 1 -> 54.6 %, 2 -> 52.6 %, 3 -> 53.8 % of the HBM roofline.
+// Measured alone (profiles/r01_stft_v3.md): 0 -> 53.4 %, 1 -> 54.6 %, 2 -> 52.6 %, 3 -> 53.8 % of the HBM roofline. Inside
+// the ingest step (power-capped) variant 1 gains 0.7 % and its slightly larger rounding error (1.3e-6 vs 7e-7 scaled)
+// flips more near-tie peaks against the double-precision oracle (15 vs 9 of 1024 tracks), so 0 stays the default.
 #ifndef AID_STFT_UNFOLD
-#define AID_STFT_UNFOLD 1
+#define AID_STFT_UNFOLD 0
 #endif
 constexpr int kUnfold = AID_STFT_UNFOLD;
 constexpr int kTwistStride = (kUnfold & 1) ? 68 : 36;  // floats per lane row of the twiddle table (16 B aligned, conflict-free LDS.128)
