@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--snr-db", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ingest-chunk", type=int, default=512)
+    ap.add_argument("--dump", default="", help="prefix of .npz files with per-window digests (debugging aid)")
     ap.add_argument("--also-queries", default="", help="comma-separated further batch sizes measured on the same index")
     ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer",
                     help="peer: k_rank stores rows into every rank's window over NVLink + device merge (aid_match_exchange_dev); "
@@ -105,6 +106,7 @@ def main():
         wins = torch.empty((n_queries, 3, 56000), dtype=torch.float32, device=dev)
         for c0 in range(0, n_queries, 2048):                        # bounded scratch: 2048 whole tracks at a time
             c1 = min(c0 + 2048, n_queries)
+            torch.cuda.synchronize()          # the engine writes `src` on its own stream: torch must be done with the last one
             src = torch.empty((c1 - c0) * samples, dtype=torch.float32, device=dev)
             for j in range(c0, c1):
                 eng.synth_tracks(src.data_ptr() + (j - c0) * samples * 4, int(q_track[j]), 1, samples, args.seed)
@@ -173,7 +175,11 @@ def main():
                     top1 += 1
                     of0 = first_off.get((best, 0))
                     offs_ok += of0 is not None and abs(of0 - q_start[q] / 128.0) <= 1.0
-        digest = int(np.bitwise_xor.reduce((m.astype(np.int64) * np.arange(1, 6)).sum(axis=2).reshape(-1) & 0xFFFFFFFF))
+        row_sums = (m.astype(np.int64) * np.arange(1, 6)).sum(axis=2)
+        digest = int(np.bitwise_xor.reduce(row_sums.reshape(-1) & 0xFFFFFFFF))
+        if args.dump and rank == 0:                      # per-window digests and the first rows, to compare runs offline
+            np.savez_compressed(f"{args.dump}_{n_queries}.npz", window_digest=np.bitwise_xor.reduce(row_sums & 0xFFFFFFFF, axis=1),
+                                n_rows=(m[:, :, 0] >= 0).sum(axis=1), first_rows=m[:, :4, :].astype(np.int32))
         per_step = {k: v[0] / args.steps for k, v in stage.items()}
         del wins
         return {"queries": n_queries, "windows_per_step": n_win, "queries_per_s": n_queries / dt, "ms_per_step": dt * 1e3,
