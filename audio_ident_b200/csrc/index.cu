@@ -48,17 +48,16 @@ __global__ void k_scatter(const uint32_t* __restrict__ hash, const uint32_t* __r
 }
 
 // ascending sort of every bucket (one thread per bucket; buckets average a few postings)
-template <class P>
-__global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, P* __restrict__ postings) {
+__global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, uint32_t* __restrict__ postings) {
     const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= kBuckets) return;
     const uint32_t b = bucket[h], e = bucket[h + 1];
     const uint32_t n = e - b;
     if (n < 2) return;
-    P* a = postings + b;
+    uint32_t* a = postings + b;
     if (n <= 32) {                                   // insertion sort
         for (uint32_t i = 1; i < n; i++) {
-            const P v = a[i];
+            const uint32_t v = a[i];
             uint32_t j = i;
             while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; j--; }
             a[j] = v;
@@ -73,24 +72,14 @@ __global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, P* __restrict
             if (a[sw] < a[child]) sw = child;
             if (child + 1 <= end && a[sw] < a[child + 1]) sw = child + 1;
             if (sw == root) return;
-            const P t = a[root]; a[root] = a[sw]; a[sw] = t;
+            const uint32_t t = a[root]; a[root] = a[sw]; a[sw] = t;
             root = sw;
         }
     };
     for (int64_t s = (int64_t)(n - 2) / 2; s >= 0; s--) sift((uint32_t)s, n - 1);
     for (uint32_t end = n - 1; end > 0; end--) {
-        const P t = a[end]; a[end] = a[0]; a[0] = t;
+        const uint32_t t = a[end]; a[end] = a[0]; a[0] = t;
         sift(0, end - 1);
-    }
-}
-
-// compaction: a segment's entries into the base's bucket ranges, postings widened to engine-wide track numbers
-__global__ void k_scatter_wide(const uint32_t* __restrict__ hash, const uint32_t* __restrict__ post, int64_t n,
-                               uint32_t first_track, uint32_t* __restrict__ cursor, uint64_t* __restrict__ postings) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t p = post[i];
-        const uint64_t track = (uint64_t)first_track + (p >> AID_POST_T_BITS);
-        postings[atomicAdd(cursor + hash[i], 1u)] = track << AID_POST_T_BITS | (p & ((1u << AID_POST_T_BITS) - 1));
     }
 }
 
@@ -116,7 +105,6 @@ void Segment::release() { st_hash.release(); st_post.release(); bucket.release()
 void aid_index_free(aid_engine*, Index* ix) {
     if (!ix) return;
     for (Segment* s : ix->segs) { s->release(); delete s; }
-    if (ix->wide) { ix->wide->release(); delete ix->wide; }
     ix->cursor.release(); ix->scan_tmp.release(); ix->d_jobs.release(); ix->d_segdesc.release();
     ix->cand.release(); ix->cand_n.release(); ix->rows.release(); ix->rows_n.release();
     delete ix;
@@ -141,10 +129,6 @@ static int set_tombstone(aid_engine* e, Index* ix, uint32_t track) {
     const uint32_t local = track % AID_SEG_TRACKS;
     s->h_tomb[local / 32] |= 1u << (local % 32);
     AID_CUDA(e, cudaMemcpy(s->tomb.as<uint32_t>() + local / 32, &s->h_tomb[local / 32], 4, cudaMemcpyHostToDevice));
-    if (ix->wide && track < ix->wide->n_tracks) {
-        ix->wide->h_tomb[track / 32] |= 1u << (track % 32);
-        AID_CUDA(e, cudaMemcpy(ix->wide->tomb.as<uint32_t>() + track / 32, &ix->wide->h_tomb[track / 32], 4, cudaMemcpyHostToDevice));
-    }
     TrackInfo& ti = ix->tracks[track];
     if (!ti.deleted) { ti.deleted = true; ix->live_tracks--; }
     return AID_OK;
@@ -222,7 +206,7 @@ static int build_segment(aid_engine* e, Index* ix, Segment* s, cudaStream_t st) 
         AID_CUDA(e, cudaMemcpyAsync(ix->cursor.p, bucket, (size_t)(kBuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
         k_scatter<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), s->st_post.as<uint32_t>(), n, ix->cursor.as<uint32_t>(),
                                         s->postings.as<uint32_t>());
-        k_bucket_sort<uint32_t><<<(unsigned)((kBuckets + 255) / 256), 256, 0, st>>>(bucket, s->postings.as<uint32_t>());
+        k_bucket_sort<<<(unsigned)((kBuckets + 255) / 256), 256, 0, st>>>(bucket, s->postings.as<uint32_t>());
         AID_CUDA(e, cudaGetLastError());
         e->launches += 6;
     }
@@ -234,23 +218,16 @@ static int build_segment(aid_engine* e, Index* ix, Segment* s, cudaStream_t st) 
 int aid_index_commit_on(aid_engine* e, cudaStream_t st) {
     Index* ix = e->index;
     for (Segment* s : ix->segs)
-        if (!s->in_base && (s->dirty || !s->bucket.p)) { int rc = build_segment(e, ix, s, st); if (rc) return rc; }
+        if (s->dirty || (!s->bucket.p)) { int rc = build_segment(e, ix, s, st); if (rc) return rc; }
     if (ix->segdesc_dirty) {
-        std::vector<aid_seg_desc> d;
-        if (ix->wide) {
-            aid_seg_desc w;
-            w.bucket = ix->wide->bucket.as<uint32_t>(); w.postings = ix->wide->postings.p; w.tomb = ix->wide->tomb.as<uint32_t>();
-            w.first_track = 0; w.n_tracks = ix->wide->n_tracks;
-            d.push_back(w);
+        std::vector<aid_seg_desc> d(ix->segs.size());
+        for (size_t i = 0; i < d.size(); i++) {
+            d[i].bucket = ix->segs[i]->bucket.as<uint32_t>();
+            d[i].postings = ix->segs[i]->postings.as<uint32_t>();
+            d[i].tomb = ix->segs[i]->tomb.as<uint32_t>();
+            d[i].first_track = ix->segs[i]->first_track;
+            d[i].n_tracks = ix->segs[i]->n_tracks;
         }
-        for (Segment* s : ix->segs) {
-            if (s->in_base) continue;
-            aid_seg_desc n;
-            n.bucket = s->bucket.as<uint32_t>(); n.postings = s->postings.p; n.tomb = s->tomb.as<uint32_t>();
-            n.first_track = s->first_track; n.n_tracks = s->n_tracks;
-            d.push_back(n);
-        }
-        ix->n_desc = (int)d.size();
         AID_CUDA(e, ix->d_segdesc.ensure(std::max<size_t>(d.size(), 1) * sizeof(aid_seg_desc)));
         AID_CUDA(e, cudaStreamSynchronize(st));
         if (!d.empty()) AID_CUDA(e, cudaMemcpy(ix->d_segdesc.p, d.data(), d.size() * sizeof(aid_seg_desc), cudaMemcpyHostToDevice));
@@ -360,72 +337,6 @@ extern "C" int aid_index_commit(aid_engine* e) {
     return AID_OK;
 }
 
-// LSM-style compaction: every full segment that is not in the base yet joins it (the base is rebuilt from the
-// segments' entry arrays: histogram over all of them, one scan, scatter with widened postings, per-bucket sort).
-extern "C" int aid_index_compact(aid_engine* e) {
-    if (!e) return AID_E_ARG;
-    AID_CUDA(e, cudaSetDevice(e->device));
-    Index* ix = e->index;
-    cudaStream_t st = e->slot[0].st;
-    uint32_t cover = 0;
-    int64_t n = 0;
-    while (cover < ix->segs.size() && ix->segs[cover]->n_tracks == AID_SEG_TRACKS &&
-           n + ix->segs[cover]->n_entries < ((int64_t)1 << 32) - 1) { n += ix->segs[cover]->n_entries; cover++; }
-    if (cover == 0 || (ix->wide && ix->wide->n_segs == cover)) {
-        int rc = aid_index_commit_on(e, st);
-        if (rc) return rc;
-        AID_CUDA(e, cudaStreamSynchronize(st));
-        return AID_OK;
-    }
-    AID_CUDA(e, cudaDeviceSynchronize());
-    if (!ix->wide) ix->wide = new WideSeg();
-    WideSeg* w = ix->wide;
-    AID_CUDA(e, w->bucket.ensure((size_t)(kBuckets + 1) * 4));
-    AID_CUDA(e, w->postings.ensure((size_t)std::max<int64_t>(n, 1) * 8));
-    AID_CUDA(e, ix->cursor.ensure((size_t)(kBuckets + 1) * 4));
-    AID_CUDA(e, ix->scan_tmp.ensure(aid_scan_tmp_elems(kBuckets + 1) * 4));
-    uint32_t* bucket = w->bucket.as<uint32_t>();
-    AID_CUDA(e, cudaMemsetAsync(bucket, 0, (size_t)(kBuckets + 1) * 4, st));
-    { StageTimer tm(e, st, 6);
-    for (uint32_t i = 0; i < cover; i++) {
-        const Segment* s = ix->segs[i];
-        if (s->n_entries == 0) continue;
-        const int grid = (int)std::min<int64_t>((s->n_entries + 255) / 256, 148 * 16);
-        k_hist<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), s->n_entries, bucket);
-        e->launches += 1;
-    }
-    AID_CUDA(e, aid_launch_scan_u32(bucket, bucket, kBuckets + 1, ix->scan_tmp.as<uint32_t>(), nullptr, nullptr, st));
-    AID_CUDA(e, cudaMemcpyAsync(ix->cursor.p, bucket, (size_t)(kBuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    for (uint32_t i = 0; i < cover; i++) {
-        const Segment* s = ix->segs[i];
-        if (s->n_entries == 0) continue;
-        const int grid = (int)std::min<int64_t>((s->n_entries + 255) / 256, 148 * 16);
-        k_scatter_wide<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), s->st_post.as<uint32_t>(), s->n_entries, s->first_track,
-                                             ix->cursor.as<uint32_t>(), w->postings.as<uint64_t>());
-        e->launches += 1;
-    }
-    k_bucket_sort<uint64_t><<<(unsigned)((kBuckets + 255) / 256), 256, 0, st>>>(bucket, w->postings.as<uint64_t>());
-    e->launches += 3; }
-    AID_CUDA(e, cudaGetLastError());
-    w->n_segs = cover; w->n_tracks = cover * AID_SEG_TRACKS; w->n_entries = n;
-    w->h_tomb.assign(w->n_tracks / 32, 0);
-    for (uint32_t t = 0; t < w->n_tracks; t++)
-        if (ix->tracks[t].deleted) w->h_tomb[t / 32] |= 1u << (t % 32);
-    AID_CUDA(e, w->tomb.ensure((size_t)w->n_tracks / 8));
-    AID_CUDA(e, cudaMemcpyAsync(w->tomb.p, w->h_tomb.data(), (size_t)w->n_tracks / 8, cudaMemcpyHostToDevice, st));
-    AID_CUDA(e, cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i < cover; i++) {          // their sorted form is no longer probed
-        Segment* s = ix->segs[i];
-        s->in_base = true; s->dirty = false;
-        s->bucket.release(); s->postings.release();
-    }
-    ix->segdesc_dirty = true;
-    int rc = aid_index_commit_on(e, st);
-    if (rc) return rc;
-    AID_CUDA(e, cudaStreamSynchronize(st));
-    return AID_OK;
-}
-
 extern "C" int aid_index_clear(aid_engine* e) {
     if (!e) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
@@ -439,9 +350,7 @@ extern "C" int aid_index_stats(aid_engine* e, int64_t* out) {
     if (!e || !out) return AID_E_ARG;
     Index* ix = e->index;
     out[0] = ix->live_tracks; out[1] = ix->n_postings; out[2] = (int64_t)ix->segs.size(); out[3] = (int64_t)ix->tracks.size();
-    out[5] = ix->wide ? (int64_t)ix->wide->n_segs : 0;
     int64_t bytes = (int64_t)ix->cursor.cap + ix->scan_tmp.cap;
-    if (ix->wide) bytes += ix->wide->bucket.cap + ix->wide->postings.cap + ix->wide->tomb.cap;
     for (Segment* s : ix->segs) bytes += s->st_hash.cap + s->st_post.cap + s->bucket.cap + s->postings.cap + s->tomb.cap;
     out[4] = bytes;
     return AID_OK;

@@ -18,26 +18,13 @@ struct Segment {
     DevBuf bucket, postings;       // sorted form
     DevBuf tomb;                   // u32[AID_SEG_TRACKS/32] deleted-track bits
     std::vector<uint32_t> h_tomb;
-    bool in_base = false;          // its entries are part of the compacted base: queries do not probe it separately
     void release();
-};
-
-// Compacted base (aid_index_compact): the entries of the first n_segs (full) segments under ONE bucket table, so a
-// query hash costs one bucket lookup and one contiguous run of postings instead of one of each per 16,384 tracks.
-// Postings are u64: (engine-wide track << AID_POST_T_BITS) | t_anchor, ordered by (hash, track, t_anchor) -- the
-// order of the segments it replaces, so results do not change. The segments keep their entry arrays (persistence).
-struct WideSeg {
-    uint32_t n_segs = 0, n_tracks = 0;
-    int64_t n_entries = 0;
-    DevBuf bucket, postings, tomb;  // u32[2^24+1], u64[n_entries], u32[n_tracks/32]
-    std::vector<uint32_t> h_tomb;
-    void release() { bucket.release(); postings.release(); tomb.release(); }
 };
 
 // what the matcher needs of a segment (device copy in Index::d_segdesc)
 struct aid_seg_desc {
     const uint32_t* bucket;
-    const void* postings;          // u32 (segment) or u64 (base; then first_track == 0)
+    const uint32_t* postings;
     const uint32_t* tomb;
     uint32_t first_track;
     uint32_t n_tracks;
@@ -47,8 +34,6 @@ struct Index {
     std::vector<TrackInfo> tracks;                       // by engine-wide track number
     std::unordered_map<std::string, uint32_t> by_name;   // live tracks only
     std::vector<Segment*> segs;
-    WideSeg* wide = nullptr;
-    int n_desc = 0;                                      // descriptors in d_segdesc: [base] + segments outside the base
     int64_t live_tracks = 0, n_postings = 0;
     DevBuf cursor, scan_tmp, d_jobs, d_segdesc;
     bool segdesc_dirty = true;

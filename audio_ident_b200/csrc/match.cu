@@ -27,22 +27,17 @@
 namespace {
 
 constexpr int kThreads = 128;
+constexpr int kSketch = 2048;
 constexpr int kTable = 256;
 constexpr int kTableMaxLoad = 192;
 constexpr int kQChunk = 512;
+constexpr int kVotesPerRound = 1024;
 constexpr int kBest = 64;                 // >= AID_MAX_ROWS, power of two
 constexpr int kSortN = 512;               // kTable + kBest <= kSortN
+constexpr uint32_t kEmpty = 0xffffffffu;
 constexpr uint64_t kPad = ~0ull;
 
-// one row candidate of a (window, segment): key = (track within the segment, or engine-wide for the base) << 18 | biased offset
-struct CandEntry { uint32_t inv_count; uint32_t tq; uint64_t key; };   // inv_count = ~count; tq = q_first | q_last << 16
-
-// The compacted base (index.h WideSeg) funnels every track's votes through one CTA per window: ~48 postings per hash at
-// a million tracks instead of ~0.8 per segment, so its sketch is larger (16-bit counters packed in pairs) and a round
-// takes more votes.
-template <bool W> struct MatchCfg;
-template <> struct MatchCfg<false> { using Post = uint32_t; static constexpr int kSketchN = 2048, kSketchWords = 2048, kRound = 1024; };
-template <> struct MatchCfg<true>  { using Post = uint64_t; static constexpr int kSketchN = 8192, kSketchWords = 4096, kRound = 8192; };
+struct CandEntry { uint32_t inv_count; uint32_t key; uint32_t tq; };   // tq = q_first | q_last << 16
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
@@ -86,11 +81,9 @@ __device__ __forceinline__ void bitonic_sort_n(uint64_t* key, uint32_t* val, int
         }
 }
 
-template <bool W>
 struct MatchSmem {
-    uint32_t sketch[MatchCfg<W>::kSketchWords];
-    typename MatchCfg<W>::Post tkey[kTable];
-    uint32_t tcnt[kTable], tmin[kTable], tmax[kTable];
+    uint32_t sketch[kSketch];
+    uint32_t tkey[kTable], tcnt[kTable], tmin[kTable], tmax[kTable];
     uint32_t qbeg[kQChunk], qadd[kQChunk], qstart[kQChunk + 1];
     uint64_t skey[kSortN];
     uint32_t sval[kSortN];
@@ -100,26 +93,19 @@ struct MatchSmem {
     uint32_t total, used, overflow, nbest, hit;
 };
 
-// Descriptors [sg0, sg0 + n_sub) of the n_seg the index has are handled by this launch (the base and the ordinary
-// segments differ in posting width); candidates of (window q, descriptor sg) go to slot q * n_seg + sg.
-template <bool W>
 __global__ void __launch_bounds__(kThreads)
 k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, const uint32_t* __restrict__ hash_off,
         const uint32_t* __restrict__ hash_len, const int32_t* __restrict__ q_status,
-        const aid_seg_desc* __restrict__ segs, int n_seg, int sg0, int n_sub,
+        const aid_seg_desc* __restrict__ segs, int n_seg,
         CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n) {
-    using Cfg = MatchCfg<W>;
-    using Post = typename Cfg::Post;
-    constexpr Post kNone = (Post)~(Post)0;
-    __shared__ MatchSmem<W> sm;
+    __shared__ MatchSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = blockIdx.x / n_sub, sg = sg0 + blockIdx.x % n_sub;
-    const int64_t out_slot = (int64_t)q * n_seg + sg;
+    const int q = blockIdx.x / n_seg, sg = blockIdx.x % n_seg;
     const aid_seg_desc seg = segs[sg];
     const uint32_t h0 = hash_off[q];
     const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : (hash_len ? hash_len[q] : hash_off[q + 1] - h0);
     const uint32_t* __restrict__ bucket = seg.bucket;
-    const Post* __restrict__ postings = static_cast<const Post*>(seg.postings);
+    const uint32_t* __restrict__ postings = seg.postings;
 
     // ---- how many votes does this (window, segment) produce?
     uint32_t mine = 0;
@@ -139,10 +125,10 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     __syncthreads();
     const uint32_t total = sm.total;
     if (total < AID_MIN_VOTES) {
-        if (tid == 0) cand_n[out_slot] = 0;
+        if (tid == 0) cand_n[blockIdx.x] = 0;
         return;
     }
-    uint32_t R = (total + Cfg::kRound - 1) / Cfg::kRound;
+    uint32_t R = (total + kVotesPerRound - 1) / kVotesPerRound;
     // Few votes (the usual case for one window against one segment): they all fit the exact table, so the sketch
     // and its second pass over the postings are skipped. If a restart is needed the sketch comes back.
     bool direct = total <= kTableMaxLoad;
@@ -150,8 +136,8 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     for (;;) {                                        // restarted with a finer partition if the exact table fills
         if (tid == 0) { sm.nbest = 0; sm.overflow = 0; }
         for (uint32_t r = 0; r < R; r++) {
-            if (!direct) for (int i = tid; i < Cfg::kSketchWords; i += kThreads) sm.sketch[i] = 0;
-            for (int i = tid; i < kTable; i += kThreads) { sm.tkey[i] = kNone; sm.tcnt[i] = 0; sm.tmin[i] = 0xffffffffu; sm.tmax[i] = 0; }
+            if (!direct) for (int i = tid; i < kSketch; i += kThreads) sm.sketch[i] = 0;
+            for (int i = tid; i < kTable; i += kThreads) { sm.tkey[i] = kEmpty; sm.tcnt[i] = 0; sm.tmin[i] = 0xffffffffu; sm.tmax[i] = 0; }
             if (tid == 0) { sm.used = 0; sm.hit = 0; }
             __syncthreads();
             for (int pass = direct ? 1 : 0; pass < 2; pass++) {
@@ -191,28 +177,21 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
                         // largest i with qstart[i] <= v
                         uint32_t lo = 0, hi = nc;
                         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; }
-                        const Post post = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
-                        const uint32_t local = (uint32_t)(post >> AID_POST_T_BITS);
+                        const uint32_t post = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
+                        const uint32_t local = post >> AID_POST_T_BITS;
                         if (seg.tomb[local >> 5] & (1u << (local & 31))) continue;
-                        const Post key = post + sm.qadd[lo];
-                        const uint32_t m = W ? mix32((uint32_t)key ^ ((uint32_t)((uint64_t)key >> 32) * 0x9e3779b9u)) : mix32((uint32_t)key);
+                        const uint32_t key = post + sm.qadd[lo];
+                        const uint32_t m = mix32(key);
                         if (R > 1 && (m >> 12) % R != r) continue;
-                        const uint32_t idx = m & (Cfg::kSketchN - 1);
-                        if constexpr (W) {                   // two 16-bit counters per word (a round has < 65536 votes)
-                            if (pass == 0) { atomicAdd(&sm.sketch[idx >> 1], 1u << (16 * (idx & 1))); continue; }
-                            if (!direct && ((sm.sketch[idx >> 1] >> (16 * (idx & 1))) & 0xffffu) < AID_MIN_VOTES) continue;
-                        } else {
-                            if (pass == 0) { atomicAdd(&sm.sketch[idx], 1u); continue; }
-                            if (!direct && sm.sketch[idx] < AID_MIN_VOTES) continue;
-                        }
+                        const uint32_t idx = m & (kSketch - 1);
+                        if (pass == 0) { atomicAdd(&sm.sketch[idx], 1u); continue; }
+                        if (!direct && sm.sketch[idx] < AID_MIN_VOTES) continue;
                         const uint32_t tq = AID_QUERY_MAX_FRAMES - sm.qadd[lo];
                         uint32_t slot = (m >> 20) & (kTable - 1);
                         for (int probe = 0; probe < kTable; probe++) {
-                            Post old;
-                            if constexpr (W) old = atomicCAS(reinterpret_cast<unsigned long long*>(&sm.tkey[slot]), (unsigned long long)kNone, (unsigned long long)key);
-                            else old = atomicCAS(&sm.tkey[slot], kNone, key);
-                            if (old == kNone) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
-                            if (old == kNone || old == key) {
+                            const uint32_t old = atomicCAS(&sm.tkey[slot], kEmpty, key);
+                            if (old == kEmpty) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
+                            if (old == kEmpty || old == key) {
                                 if (atomicAdd(&sm.tcnt[slot], 1u) + 1 == AID_MIN_VOTES) sm.hit = 1;   // a row is born
                                 atomicMin(&sm.tmin[slot], tq);
                                 atomicMax(&sm.tmax[slot], tq);
@@ -232,9 +211,8 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
             for (int i = tid; i < kSortN; i += kThreads) {
                 uint64_t k = kPad; uint32_t v = 0;
                 if (i < kTable) {
-                    if (sm.tkey[i] != kNone && sm.tcnt[i] >= AID_MIN_VOTES) {
-                        // 20-bit inverted count above a 44-bit key (26-bit track, 18-bit biased offset)
-                        k = ((uint64_t)(0xfffffu - min(sm.tcnt[i], 0xfffffu)) << 44) | (uint64_t)sm.tkey[i];
+                    if (sm.tkey[i] != kEmpty && sm.tcnt[i] >= AID_MIN_VOTES) {
+                        k = ((uint64_t)(0xffffffffu - sm.tcnt[i]) << 32) | sm.tkey[i];
                         v = (sm.tmin[i] & 0xffffu) | (sm.tmax[i] << 16);
                     }
                 } else if (i - kTable < (int)nb) { k = sm.bkey[i - kTable]; v = sm.bval[i - kTable]; }
@@ -257,15 +235,15 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     }
 
     const uint32_t n = min(sm.nbest, (uint32_t)AID_MAX_ROWS);
-    CandEntry* out = cand + out_slot * AID_MAX_ROWS;
+    CandEntry* out = cand + (int64_t)blockIdx.x * AID_MAX_ROWS;
     if (tid < (int)n) {
         CandEntry c;
-        c.inv_count = 0xffffffffu - (0xfffffu - (uint32_t)(sm.bkey[tid] >> 44));
-        c.key = sm.bkey[tid] & (((uint64_t)1 << 44) - 1);
+        c.inv_count = (uint32_t)(sm.bkey[tid] >> 32);
+        c.key = (uint32_t)sm.bkey[tid];
         c.tq = sm.bval[tid];
         out[tid] = c;
     }
-    if (tid == 0) cand_n[out_slot] = n;
+    if (tid == 0) cand_n[blockIdx.x] = n;
 }
 
 // ---- per query: merge the segments' lists, order by (count desc, track asc, offset asc), write rows
@@ -296,7 +274,7 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
                 const CandEntry c = cand[ci];
                 const uint64_t inv = c.inv_count - (0xffffffffu - 0xfffffu);          // 20-bit inverted count
                 const uint64_t track = (uint64_t)segs[sg].first_track + (c.key >> AID_POST_T_BITS);
-                const uint64_t off = c.key & (((uint64_t)1 << AID_POST_T_BITS) - 1);
+                const uint64_t off = c.key & ((1u << AID_POST_T_BITS) - 1);
                 skey[base + tid] = ((c.inv_count <= 0xffffffffu - 0xfffffu ? 0ull : inv) << 44) | (track << 19) | off;
                 sval[base + tid] = (uint32_t)ci;
             }
@@ -322,8 +300,8 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
         const CandEntry c = cand[sval[tid]];
         const uint32_t sgi = (uint32_t)((sval[tid] / AID_MAX_ROWS) % n_seg);
         r.count = (int32_t)(0xffffffffu - c.inv_count);
-        r.track = segs[sgi].first_track + (uint32_t)(c.key >> AID_POST_T_BITS);
-        r.offset = (int32_t)(c.key & (((uint64_t)1 << AID_POST_T_BITS) - 1)) - AID_QUERY_MAX_FRAMES;
+        r.track = segs[sgi].first_track + (c.key >> AID_POST_T_BITS);
+        r.offset = (int32_t)(c.key & ((1u << AID_POST_T_BITS) - 1)) - AID_QUERY_MAX_FRAMES;
         r.q_first = (int32_t)(c.tq & 0xffffu);
         r.q_last = (int32_t)(c.tq >> 16);
     }
@@ -367,8 +345,7 @@ int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* 
     Index* ix = e->index;
     int rc = aid_index_commit_on(e, st);
     if (rc) return rc;
-    const int n_seg = ix->n_desc;                    // [base] + the segments outside it
-    const int n_wide = ix->wide ? 1 : 0;
+    const int n_seg = (int)ix->segs.size();
     if (n_q == 0) return AID_OK;
     if (n_seg == 0) {
         if (sink.lay.world == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
@@ -383,18 +360,13 @@ int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* 
     AID_CUDA(e, ix->cand.ensure((size_t)n_cta * AID_MAX_ROWS * sizeof(CandEntry)));
     AID_CUDA(e, ix->cand_n.ensure((size_t)n_cta * 4));
     { StageTimer tm(e, st, 4);
-    if (n_wide)
-        k_match<true><<<(unsigned)n_q, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_segdesc.as<aid_seg_desc>(),
-                                                          n_seg, 0, 1, ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>());
-    if (n_seg > n_wide)
-        k_match<false><<<(unsigned)((int64_t)n_q * (n_seg - n_wide)), kThreads, 0, st>>>(
-            d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg, n_wide, n_seg - n_wide,
-            ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>()); }
+    k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
+                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>()); }
     { StageTimer tm(e, st, 5);
     k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
                                      max_rows, d_rows, d_n_rows, sink); }
     AID_CUDA(e, cudaGetLastError());
-    e->launches += 1 + (n_wide ? 1 : 0) + (n_seg > n_wide ? 1 : 0);
+    e->launches += 2;
     return AID_OK;
 }
 

@@ -236,10 +236,6 @@ class Engine:
     def index_commit(self) -> None:
         self._check(self._L.aid_index_commit(self._h))
 
-    def index_compact(self) -> None:
-        """Merges all full segments into one base with a single hash table (aid_index_compact); rows do not change."""
-        self._check(self._L.aid_index_compact(self._h))
-
     def index_clear(self) -> None:
         self._check(self._L.aid_index_clear(self._h))
 
@@ -247,7 +243,7 @@ class Engine:
         out = np.zeros(8, np.int64)
         self._check(self._L.aid_index_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return {"tracks": int(out[0]), "postings": int(out[1]), "segments": int(out[2]),
-                "tracks_total": int(out[3]), "device_bytes": int(out[4]), "segments_in_base": int(out[5])}
+                "tracks_total": int(out[3]), "device_bytes": int(out[4])}
 
     def track_name(self, track: int) -> str:
         buf = C.create_string_buffer(256)

@@ -137,14 +137,8 @@ int aid_index_delete(aid_engine* e, const char* name);
 /* makes every added track searchable now (otherwise done lazily by the next query) */
 int aid_index_commit(aid_engine* e);
 int aid_index_clear(aid_engine* e);
-/* Compaction. Tracks are stored in segments of AID_SEG_TRACKS (16,384), each with its own hash table, so that adding
- * a track rebuilds only the open segment; a query probes every segment. aid_index_compact merges all full segments
- * into one base with a single hash table (64-bit postings carrying the engine-wide track number): a query hash then
- * costs one table lookup and one contiguous run of postings instead of one of each per segment. Rows are identical
- * before and after; later adds go to new segments (compact again when enough have filled); deletes still work. */
-int aid_index_compact(aid_engine* e);
-/* out[8]: [0] live tracks, [1] postings, [2] segments, [3] tracks incl. deleted, [4] device bytes held by the index,
- * [5] segments merged into the compacted base */
+/* out[0] = live tracks, out[1] = postings, out[2] = segments, out[3] = tracks incl. deleted,
+ * out[4] = device bytes held by the index */
 int aid_index_stats(aid_engine* e, int64_t* out);
 /* name of track number `track`; returns its length or a negative aid_status */
 int aid_index_track_name(aid_engine* e, uint32_t track, char* buf, int buf_len);
