@@ -47,14 +47,9 @@ __global__ void k_scatter(const uint32_t* __restrict__ hash, const uint32_t* __r
         postings[atomicAdd(cursor + hash[i], 1u)] = post[i];
 }
 
-// ascending sort of every bucket (one thread per bucket; buckets average a few postings)
-__global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, uint32_t* __restrict__ postings) {
-    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= kBuckets) return;
-    const uint32_t b = bucket[h], e = bucket[h + 1];
-    const uint32_t n = e - b;
+// ascending in-place sort of one short run of postings
+__device__ void sort_run(uint32_t* a, uint32_t n) {
     if (n < 2) return;
-    uint32_t* a = postings + b;
     if (n <= 32) {                                   // insertion sort
         for (uint32_t i = 1; i < n; i++) {
             const uint32_t v = a[i];
@@ -83,6 +78,60 @@ __global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, uint32_t* __r
     }
 }
 
+// every bucket of a segment (one thread per bucket; buckets average a few postings)
+__global__ void k_bucket_sort(const uint32_t* __restrict__ bucket, uint32_t* __restrict__ postings) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= kBuckets) return;
+    const uint32_t b = bucket[h];
+    sort_run(postings + b, bucket[h + 1] - b);
+}
+
+// ---- segment groups (index.h SegGroup): directory entry of hash h = dir[8 h .. 8 h + 8): start, 4 words of 16-bit counts
+__device__ __forceinline__ uint32_t dir_count(const uint32_t* __restrict__ ent, int sub) {
+    return (ent[1 + (sub >> 1)] >> (16 * (sub & 1))) & 0xffffu;
+}
+
+__global__ void k_group_hist(const uint32_t* __restrict__ hash, int64_t n, int sub, uint32_t* __restrict__ dir,
+                             uint32_t* __restrict__ overflow) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t old = atomicAdd(dir + (size_t)hash[i] * 8 + 1 + (sub >> 1), 1u << (16 * (sub & 1)));
+        if (((old >> (16 * (sub & 1))) & 0xffffu) == 0xffffu) *overflow = 1;     // a 16-bit count wrapped: the group is abandoned
+    }
+}
+
+__global__ void k_group_total(const uint32_t* __restrict__ dir, uint32_t* __restrict__ total) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h > kBuckets) return;
+    uint32_t t = 0;
+    if (h < kBuckets)
+        for (int s = 0; s < kGroupSegs; s++) t += dir_count(dir + (size_t)h * 8, s);
+    total[h] = t;
+}
+
+// after the scan: start of every hash into the directory, and the scatter cursor of member `sub`
+__global__ void k_group_cursor(uint32_t* __restrict__ dir, const uint32_t* __restrict__ start, int sub, int write_start,
+                               uint32_t* __restrict__ cursor) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= kBuckets) return;
+    uint32_t* ent = dir + (size_t)h * 8;
+    uint32_t c = start[h];
+    if (write_start) ent[0] = c;
+    for (int s = 0; s < sub; s++) c += dir_count(ent, s);
+    cursor[h] = c;
+}
+
+__global__ void k_group_sort(const uint32_t* __restrict__ dir, int n_segs, uint32_t* __restrict__ postings) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= kBuckets) return;
+    const uint32_t* ent = dir + (size_t)h * 8;
+    uint32_t b = ent[0];
+    for (int s = 0; s < n_segs; s++) {
+        const uint32_t n = dir_count(ent, s);
+        sort_run(postings + b, n);
+        b += n;
+    }
+}
+
 cudaError_t grow_copy(DevBuf& b, size_t used_bytes, size_t need_bytes) {
     if (need_bytes <= b.cap) return cudaSuccess;
     size_t want = std::max(need_bytes, b.cap * 2);
@@ -105,7 +154,8 @@ void Segment::release() { st_hash.release(); st_post.release(); bucket.release()
 void aid_index_free(aid_engine*, Index* ix) {
     if (!ix) return;
     for (Segment* s : ix->segs) { s->release(); delete s; }
-    ix->cursor.release(); ix->scan_tmp.release(); ix->d_jobs.release(); ix->d_segdesc.release();
+    for (SegGroup* g : ix->groups) { if (g) { g->release(); delete g; } }
+    ix->cursor.release(); ix->scan_tmp.release(); ix->d_jobs.release(); ix->d_segdesc.release(); ix->group_start.release();
     ix->cand.release(); ix->cand_n.release(); ix->rows.release(); ix->rows_n.release();
     delete ix;
 }
@@ -127,6 +177,7 @@ static Segment* open_segment(aid_engine* e, Index* ix) {
 static int set_tombstone(aid_engine* e, Index* ix, uint32_t track) {
     Segment* s = ix->segs[track / AID_SEG_TRACKS];
     const uint32_t local = track % AID_SEG_TRACKS;
+    if (!(s->h_tomb[local / 32] & (1u << (local % 32)))) { s->n_deleted++; ix->segdesc_dirty = true; }
     s->h_tomb[local / 32] |= 1u << (local % 32);
     AID_CUDA(e, cudaMemcpy(s->tomb.as<uint32_t>() + local / 32, &s->h_tomb[local / 32], 4, cudaMemcpyHostToDevice));
     TrackInfo& ti = ix->tracks[track];
@@ -215,18 +266,99 @@ static int build_segment(aid_engine* e, Index* ix, Segment* s, cudaStream_t st) 
     return AID_OK;
 }
 
+// (Re)builds group k over its sealed member segments [first, first + n). Returns AID_OK with *built = false when a
+// 16-bit count would overflow (degenerate corpus): the members then stay plain segments.
+static int build_group(aid_engine* e, Index* ix, SegGroup* g, cudaStream_t st, bool* built) {
+    *built = false;
+    int64_t n = 0;
+    for (uint32_t i = 0; i < g->n_segs; i++) n += ix->segs[g->first_seg + i]->n_entries;
+    if (n >= ((int64_t)1 << 32) - 1) return AID_OK;
+    AID_CUDA(e, g->dir.ensure((size_t)kBuckets * 32));
+    AID_CUDA(e, g->postings.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    AID_CUDA(e, ix->cursor.ensure((size_t)(kBuckets + 1) * 4));
+    AID_CUDA(e, ix->group_start.ensure((size_t)(kBuckets + 1) * 4 + 256));
+    AID_CUDA(e, ix->scan_tmp.ensure(aid_scan_tmp_elems(kBuckets + 1) * 4));
+    uint32_t* dir = g->dir.as<uint32_t>();
+    uint32_t* start = ix->group_start.as<uint32_t>();
+    uint32_t* overflow = start + kBuckets + 1;
+    AID_CUDA(e, cudaMemsetAsync(dir, 0, (size_t)kBuckets * 32, st));
+    AID_CUDA(e, cudaMemsetAsync(overflow, 0, 4, st));
+    { StageTimer tm(e, st, 6);
+    const unsigned per_hash = (unsigned)((kBuckets + 1 + 255) / 256);
+    for (uint32_t i = 0; i < g->n_segs; i++) {
+        const Segment* s = ix->segs[g->first_seg + i];
+        if (s->n_entries == 0) continue;
+        const int grid = (int)std::min<int64_t>((s->n_entries + 255) / 256, 148 * 16);
+        k_group_hist<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), s->n_entries, (int)i, dir, overflow);
+        e->launches += 1;
+    }
+    uint32_t h_overflow = 0;
+    AID_CUDA(e, cudaMemcpyAsync(&h_overflow, overflow, 4, cudaMemcpyDeviceToHost, st));
+    AID_CUDA(e, cudaStreamSynchronize(st));
+    if (h_overflow) { g->release(); return AID_OK; }
+    k_group_total<<<per_hash, 256, 0, st>>>(dir, start);
+    AID_CUDA(e, aid_launch_scan_u32(start, start, kBuckets + 1, ix->scan_tmp.as<uint32_t>(), nullptr, nullptr, st));
+    for (uint32_t i = 0; i < g->n_segs; i++) {
+        const Segment* s = ix->segs[g->first_seg + i];
+        k_group_cursor<<<per_hash, 256, 0, st>>>(dir, start, (int)i, i == 0, ix->cursor.as<uint32_t>());
+        if (s->n_entries > 0) {
+            const int grid = (int)std::min<int64_t>((s->n_entries + 255) / 256, 148 * 16);
+            k_scatter<<<grid, 256, 0, st>>>(s->st_hash.as<uint32_t>(), s->st_post.as<uint32_t>(), s->n_entries,
+                                            ix->cursor.as<uint32_t>(), g->postings.as<uint32_t>());
+        }
+        e->launches += 2;
+    }
+    k_group_sort<<<(unsigned)((kBuckets + 255) / 256), 256, 0, st>>>(dir, (int)g->n_segs, g->postings.as<uint32_t>());
+    e->launches += 4; }
+    AID_CUDA(e, cudaGetLastError());
+    g->n_entries = n;
+    *built = true;
+    return AID_OK;
+}
+
 int aid_index_commit_on(aid_engine* e, cudaStream_t st) {
     Index* ix = e->index;
+    // 1. sealed (full) segments join the group of their octet; a group is rebuilt when it gains a member
+    if (ix->grouping) {
+        const size_t n_groups = (ix->segs.size() + kGroupSegs - 1) / kGroupSegs;
+        if (ix->groups.size() < n_groups) ix->groups.resize(n_groups, nullptr);
+        for (size_t k = 0; k < n_groups; k++) {
+            uint32_t sealed = 0;
+            while (sealed < (uint32_t)kGroupSegs && k * kGroupSegs + sealed < ix->segs.size() &&
+                   ix->segs[k * kGroupSegs + sealed]->n_tracks == AID_SEG_TRACKS) sealed++;
+            SegGroup* g = ix->groups[k];
+            if (sealed == 0 || (g && (g->n_segs == sealed || g->n_segs == 0xffffffffu))) continue;
+            if (!g) { g = new SegGroup(); ix->groups[k] = g; }
+            g->first_seg = (uint32_t)(k * kGroupSegs); g->n_segs = sealed;
+            bool built = false;
+            int rc = build_group(e, ix, g, st, &built);
+            if (rc) return rc;
+            if (!built) { g->n_segs = 0xffffffffu; continue; }          // not groupable: do not try again
+            AID_CUDA(e, cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < sealed; i++) {
+                Segment* s = ix->segs[g->first_seg + i];
+                s->group = (int)k; s->sub = (int)i; s->dirty = false;
+                s->bucket.release(); s->postings.release();
+            }
+            ix->segdesc_dirty = true;
+        }
+    }
+    // 2. everything else keeps its own table
     for (Segment* s : ix->segs)
-        if (s->dirty || (!s->bucket.p)) { int rc = build_segment(e, ix, s, st); if (rc) return rc; }
+        if (s->group < 0 && (s->dirty || !s->bucket.p)) { int rc = build_segment(e, ix, s, st); if (rc) return rc; }
     if (ix->segdesc_dirty) {
         std::vector<aid_seg_desc> d(ix->segs.size());
         for (size_t i = 0; i < d.size(); i++) {
-            d[i].bucket = ix->segs[i]->bucket.as<uint32_t>();
-            d[i].postings = ix->segs[i]->postings.as<uint32_t>();
-            d[i].tomb = ix->segs[i]->tomb.as<uint32_t>();
-            d[i].first_track = ix->segs[i]->first_track;
-            d[i].n_tracks = ix->segs[i]->n_tracks;
+            const Segment* s = ix->segs[i];
+            const SegGroup* g = s->group >= 0 ? ix->groups[s->group] : nullptr;
+            d[i].bucket = g ? nullptr : s->bucket.as<uint32_t>();
+            d[i].postings = g ? g->postings.as<uint32_t>() : s->postings.as<uint32_t>();
+            d[i].dir = g ? g->dir.as<uint32_t>() : nullptr;
+            d[i].sub = (uint32_t)s->sub;
+            d[i].tomb = s->tomb.as<uint32_t>();
+            d[i].first_track = s->first_track;
+            d[i].n_tracks = s->n_tracks;
+            d[i].n_deleted = s->n_deleted;
         }
         AID_CUDA(e, ix->d_segdesc.ensure(std::max<size_t>(d.size(), 1) * sizeof(aid_seg_desc)));
         AID_CUDA(e, cudaStreamSynchronize(st));
@@ -341,8 +473,26 @@ extern "C" int aid_index_clear(aid_engine* e) {
     if (!e) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
     AID_CUDA(e, cudaDeviceSynchronize());
+    const bool grouping = e->index->grouping;
     aid_index_free(e, e->index);
     e->index = aid_index_new();
+    e->index->grouping = grouping;
+    return AID_OK;
+}
+
+extern "C" int aid_index_set_grouping(aid_engine* e, int on) {
+    if (!e) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Index* ix = e->index;
+    if (ix->grouping == (on != 0)) return AID_OK;
+    AID_CUDA(e, cudaDeviceSynchronize());
+    ix->grouping = on != 0;
+    if (!on) {                                   // back to plain segments: their tables are rebuilt by the next commit
+        for (SegGroup* g : ix->groups) if (g) { g->release(); delete g; }
+        ix->groups.clear();
+        for (Segment* s : ix->segs) if (s->group >= 0) { s->group = -1; s->sub = 0; s->dirty = true; }
+    }
+    ix->segdesc_dirty = true;
     return AID_OK;
 }
 
@@ -352,6 +502,10 @@ extern "C" int aid_index_stats(aid_engine* e, int64_t* out) {
     out[0] = ix->live_tracks; out[1] = ix->n_postings; out[2] = (int64_t)ix->segs.size(); out[3] = (int64_t)ix->tracks.size();
     int64_t bytes = (int64_t)ix->cursor.cap + ix->scan_tmp.cap;
     for (Segment* s : ix->segs) bytes += s->st_hash.cap + s->st_post.cap + s->bucket.cap + s->postings.cap + s->tomb.cap;
+    int64_t grouped = 0;
+    for (SegGroup* g : ix->groups) if (g && g->dir.p) { bytes += g->dir.cap + g->postings.cap; grouped += g->n_segs; }
+    bytes += ix->group_start.cap;
+    out[5] = grouped;
     out[4] = bytes;
     return AID_OK;
 }
@@ -443,7 +597,7 @@ extern "C" int aid_index_load(aid_engine* e, const char* dir) {
         s->h_tomb.assign(AID_SEG_TRACKS / 32, 0);
         ix->segs.push_back(s);
         for (uint32_t l = 0; l < nt; l++)
-            if (s->first_track + l < ix->tracks.size() && ix->tracks[s->first_track + l].deleted) s->h_tomb[l / 32] |= 1u << (l % 32);
+            if (s->first_track + l < ix->tracks.size() && ix->tracks[s->first_track + l].deleted) { s->h_tomb[l / 32] |= 1u << (l % 32); s->n_deleted++; }
         cudaError_t ce = s->tomb.ensure(AID_SEG_TRACKS / 8);
         if (ce == cudaSuccess) ce = cudaMemcpy(s->tomb.p, s->h_tomb.data(), AID_SEG_TRACKS / 8, cudaMemcpyHostToDevice);
         buf.resize((size_t)n);

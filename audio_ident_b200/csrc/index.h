@@ -18,24 +18,45 @@ struct Segment {
     DevBuf bucket, postings;       // sorted form
     DevBuf tomb;                   // u32[AID_SEG_TRACKS/32] deleted-track bits
     std::vector<uint32_t> h_tomb;
+    uint32_t n_deleted = 0;        // tombstones set
+    int group = -1, sub = 0;       // member `sub` of Index::groups[group] once sealed and grouped (then bucket/postings are released)
     void release();
+};
+
+// Up to kGroupSegs sealed (full) segments share one hash directory: per hash one 32-byte entry
+//   u32 start | u16 count[8] | 12 B pad
+// and one posting array ordered by (hash, member segment, local track, t_anchor). A (window, segment) CTA of the
+// matcher reads ONE sector per query hash -- the same sector its 7 sibling CTAs read, so 7 of 8 lookups are L2 hits --
+// and the posting runs of the 8 members of a hash are adjacent (they share sectors too). Votes, keys, tombstones and
+// results are exactly those of the plain segments; only where a segment's run of a hash is found changes.
+constexpr int kGroupSegs = 8;
+struct SegGroup {
+    uint32_t first_seg = 0, n_segs = 0;
+    int64_t n_entries = 0;
+    DevBuf dir, postings;          // u32[2^24][8], u32[n_entries]
+    void release() { dir.release(); postings.release(); }
 };
 
 // what the matcher needs of a segment (device copy in Index::d_segdesc)
 struct aid_seg_desc {
-    const uint32_t* bucket;
-    const uint32_t* postings;
+    const uint32_t* bucket;        // plain segment: u32[2^24+1]; null for a grouped one
+    const uint32_t* postings;      // the segment's or its group's posting array
     const uint32_t* tomb;
+    const uint32_t* dir;           // grouped segment: the group's directory
+    uint32_t sub;                  // ... and which member this segment is
     uint32_t first_track;
     uint32_t n_tracks;
+    uint32_t n_deleted;            // 0: the matcher skips the tombstone lookup
 };
 
 struct Index {
     std::vector<TrackInfo> tracks;                       // by engine-wide track number
     std::unordered_map<std::string, uint32_t> by_name;   // live tracks only
     std::vector<Segment*> segs;
+    std::vector<SegGroup*> groups;                       // groups[k] covers the sealed segments among [8k, 8k + 8)
+    bool grouping = true;                                // aid_index_set_grouping (tests and A/B measurements)
     int64_t live_tracks = 0, n_postings = 0;
-    DevBuf cursor, scan_tmp, d_jobs, d_segdesc;
+    DevBuf cursor, scan_tmp, d_jobs, d_segdesc, group_start;
     bool segdesc_dirty = true;
     // matcher workspace
     DevBuf cand, cand_n, rows, rows_n;

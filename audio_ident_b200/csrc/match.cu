@@ -106,24 +106,80 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : (hash_len ? hash_len[q] : hash_off[q + 1] - h0);
     const uint32_t* __restrict__ bucket = seg.bucket;
     const uint32_t* __restrict__ postings = seg.postings;
+    const bool any_deleted = seg.n_deleted != 0;          // no tombstone lookup (a dependent load per vote) in clean segments
+    // Where this segment keeps the postings of hash h. A plain segment has its own table of 2^24 + 1 offsets; a grouped
+    // one (index.h SegGroup) shares a directory with up to 7 siblings: one 32-byte entry per hash, the same sector for
+    // the sibling CTAs of this window (L2 hits), and sibling runs of a hash are adjacent in the posting array.
+    const uint32_t* __restrict__ dir = seg.dir;
+    const uint32_t sub = seg.sub;
+    auto run_of = [&](uint32_t h, uint32_t& lo) -> uint32_t {
+        if (dir) {
+            const uint4 a = *reinterpret_cast<const uint4*>(dir + (size_t)h * 8);
+            const uint32_t c67 = dir[(size_t)h * 8 + 4];
+            const uint32_t w[4] = {a.y, a.z, a.w, c67};
+            uint32_t at = a.x;
+            for (uint32_t j = 0; j < sub; j++) at += (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            lo = at;
+            return (w[sub >> 1] >> (16 * (sub & 1))) & 0xffffu;
+        }
+        lo = bucket[h];
+        return bucket[h + 1] - lo;
+    };
 
-    // ---- how many votes does this (window, segment) produce?
-    uint32_t mine = 0;
-    for (uint32_t i = tid; i < nh; i += kThreads) {
-        const uint32_t h = q_hash[h0 + i];
-        mine += bucket[h + 1] - bucket[h];
-    }
+    // Stages hashes [c0, c0 + nc) of the window: bucket begin, time bias and the exclusive prefix of the bucket lengths,
+    // so that the votes of the chunk form one flat list; returns their number (the same in every thread).
+    auto stage = [&](uint32_t c0, uint32_t nc) -> uint32_t {
+        uint32_t run = 0;                       // votes of earlier strides of this chunk
+        for (uint32_t b = 0; b < nc; b += kThreads) {
+            const uint32_t i = b + tid;
+            uint32_t len = 0;
+            if (i < nc) {
+                uint32_t lo;
+                len = run_of(q_hash[h0 + c0 + i], lo);
+                sm.qbeg[i] = lo;
+                sm.qadd[i] = AID_QUERY_MAX_FRAMES - q_t[h0 + c0 + i];
+            }
+            uint32_t incl = len;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(AID_FULL_MASK, mine, d);
-    if (lane == 0) sm.wsum[warp] = mine;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kThreads / 32; w++) t += sm.wsum[w];
-        sm.total = t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(AID_FULL_MASK, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) sm.wsum[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, all = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = sm.wsum[w]; all += c; before += w < warp ? c : 0; }
+            if (i < nc) sm.qstart[i] = run + before + incl - len;
+            run += all;
+            __syncthreads();
+        }
+        if (tid == 0) sm.qstart[nc] = run;
+        __syncthreads();
+        return run;
+    };
+
+    // ---- how many votes does this (window, segment) produce? A window that fits one chunk (the usual case: a 3.5 s
+    // window has ~300 hashes) is staged once, here, and its bucket table entries are read once for all passes.
+    const bool single = nh <= (uint32_t)kQChunk;
+    uint32_t total;
+    if (single) {
+        total = stage(0, nh);
+    } else {
+        uint32_t mine = 0;
+        for (uint32_t i = tid; i < nh; i += kThreads) { uint32_t lo; mine += run_of(q_hash[h0 + i], lo); }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(AID_FULL_MASK, mine, d);
+        if (lane == 0) sm.wsum[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kThreads / 32; w++) t += sm.wsum[w];
+            sm.total = t;
+        }
+        __syncthreads();
+        total = sm.total;
     }
-    __syncthreads();
-    const uint32_t total = sm.total;
     if (total < AID_MIN_VOTES) {
         if (tid == 0) cand_n[blockIdx.x] = 0;
         return;
@@ -143,43 +199,14 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
             for (int pass = direct ? 1 : 0; pass < 2; pass++) {
                 for (uint32_t c0 = 0; c0 < nh; c0 += kQChunk) {
                     const uint32_t nc = min((uint32_t)kQChunk, nh - c0);
-                    // stage the chunk: bucket begin, length prefix, time bias
-                    uint32_t run = 0;           // votes of earlier strides of this chunk
-                    for (uint32_t b = 0; b < nc; b += kThreads) {
-                        const uint32_t i = b + tid;
-                        uint32_t len = 0;
-                        if (i < nc) {
-                            const uint32_t h = q_hash[h0 + c0 + i];
-                            const uint32_t lo = bucket[h];
-                            len = bucket[h + 1] - lo;
-                            sm.qbeg[i] = lo;
-                            sm.qadd[i] = AID_QUERY_MAX_FRAMES - q_t[h0 + c0 + i];
-                        }
-                        uint32_t incl = len;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const uint32_t o = __shfl_up_sync(AID_FULL_MASK, incl, d);
-                            if (lane >= d) incl += o;
-                        }
-                        if (lane == 31) sm.wsum[warp] = incl;
-                        __syncthreads();
-                        uint32_t before = 0, all = 0;
-#pragma unroll
-                        for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = sm.wsum[w]; all += c; before += w < warp ? c : 0; }
-                        if (i < nc) sm.qstart[i] = run + before + incl - len;
-                        run += all;
-                        __syncthreads();
-                    }
-                    if (tid == 0) sm.qstart[nc] = run;
-                    __syncthreads();
-                    const uint32_t nv = run;
+                    const uint32_t nv = single ? total : stage(c0, nc);
                     for (uint32_t v = tid; v < nv; v += kThreads) {
                         // largest i with qstart[i] <= v
                         uint32_t lo = 0, hi = nc;
                         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; }
                         const uint32_t post = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
                         const uint32_t local = post >> AID_POST_T_BITS;
-                        if (seg.tomb[local >> 5] & (1u << (local & 31))) continue;
+                        if (any_deleted && (seg.tomb[local >> 5] & (1u << (local & 31)))) continue;
                         const uint32_t key = post + sm.qadd[lo];
                         const uint32_t m = mix32(key);
                         if (R > 1 && (m >> 12) % R != r) continue;

@@ -236,6 +236,10 @@ class Engine:
     def index_commit(self) -> None:
         self._check(self._L.aid_index_commit(self._h))
 
+    def index_set_grouping(self, on: bool) -> None:
+        """Full segments share a hash directory eight at a time (default) or keep one table each; rows are the same."""
+        self._check(self._L.aid_index_set_grouping(self._h, int(bool(on))))
+
     def index_clear(self) -> None:
         self._check(self._L.aid_index_clear(self._h))
 
@@ -243,7 +247,7 @@ class Engine:
         out = np.zeros(8, np.int64)
         self._check(self._L.aid_index_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return {"tracks": int(out[0]), "postings": int(out[1]), "segments": int(out[2]),
-                "tracks_total": int(out[3]), "device_bytes": int(out[4])}
+                "tracks_total": int(out[3]), "device_bytes": int(out[4]), "segments_grouped": int(out[5])}
 
     def track_name(self, track: int) -> str:
         buf = C.create_string_buffer(256)

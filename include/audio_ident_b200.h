@@ -137,8 +137,13 @@ int aid_index_delete(aid_engine* e, const char* name);
 /* makes every added track searchable now (otherwise done lazily by the next query) */
 int aid_index_commit(aid_engine* e);
 int aid_index_clear(aid_engine* e);
-/* out[0] = live tracks, out[1] = postings, out[2] = segments, out[3] = tracks incl. deleted,
- * out[4] = device bytes held by the index */
+/* Tracks live in segments of AID_SEG_TRACKS (16,384), the unit of incremental build and of vote parallelism. Full
+ * segments are grouped eight at a time under one hash directory (one 32-byte entry per hash: start + eight 16-bit run
+ * lengths) so that the eight CTAs probing them for a window share every directory sector and posting sector. Rows do
+ * not depend on the grouping; on = 1 is the default, 0 keeps one table per segment (tests, A/B measurements). */
+int aid_index_set_grouping(aid_engine* e, int on);
+/* out[8]: [0] live tracks, [1] postings, [2] segments, [3] tracks incl. deleted, [4] device bytes held by the index,
+ * [5] segments that share a group directory */
 int aid_index_stats(aid_engine* e, int64_t* out);
 /* name of track number `track`; returns its length or a negative aid_status */
 int aid_index_track_name(aid_engine* e, uint32_t track, char* buf, int buf_len);

@@ -151,3 +151,90 @@ def test_empty_and_degenerate_queries(fresh_index, corpus):
     pcm, off = ragged([np.zeros(0, np.float32), np.zeros(800, np.float32), np.zeros(16000, np.float32), tracks[0][:48000]])
     rows, n = eng.query(pcm, off)
     assert list(n[:3]) == [0, 0, 0] and n[3] >= 1 and rows[3]["track"][0] == 0 and rows[3]["offset"][0] == 0
+
+
+def _tiny_corpus(n_tracks, per_track, hash_space, seed):
+    """synthetic fingerprints: per_track (hash, t) pairs per track, hashes from a small space so that buckets are deep"""
+    rng = np.random.default_rng(seed)
+    h = rng.integers(0, hash_space, n_tracks * per_track, dtype=np.int64).astype(np.uint32)
+    t = np.sort(rng.integers(0, 3000, (n_tracks, per_track)), axis=1).reshape(-1).astype(np.uint32)
+    off = np.arange(n_tracks + 1, dtype=np.int64) * per_track
+    return h, t, off
+
+
+def test_segment_groups_keep_rows_bit_exact(fresh_index, oracle, tmp_path):
+    """Full segments share a hash directory eight at a time (index.h SegGroup). 40,000 tracks = two full segments
+    (grouped) + a partial one (its own table). Rows must equal the oracle's global index with and without grouping, and
+    deletes, later adds (a third segment fills up and joins the group) and save + load must keep working. Deep buckets
+    (~190 postings per hash) push the matcher through several sketch rounds and table restarts."""
+    eng = fresh_index
+    eng.index_set_grouping(True)
+    NT, PER, SPACE = 40000, 24, 5000
+    h, t, off = _tiny_corpus(NT, PER, SPACE, 7)
+    # copies of track 5 in the other full segment and in the partial one: equal counts, ordered by track
+    for g in (20000, 39000, 39001):
+        h[g * PER:(g + 1) * PER] = h[5 * PER:6 * PER]; t[g * PER:(g + 1) * PER] = t[5 * PER:6 * PER]
+    for c0 in range(0, NT, 8192):
+        c1 = min(c0 + 8192, NT)
+        ok = eng.index_add_hashes(h[off[c0]:off[c1]], t[off[c0]:off[c1]], off[c0:c1 + 1] - off[c0], [4000] * (c1 - c0),
+                                  [str(g) for g in range(c0, c1)])
+        assert ok.all()
+    track_of = np.repeat(np.arange(NT, dtype=np.uint32), PER)
+    ix = oracle.Index(h, track_of, t)
+
+    rng = np.random.default_rng(11)
+    picks = [5, 16383, 16384, 32767, 32768, 39999] + [int(g) for g in rng.integers(0, NT, 26)]
+    qh, qt, qoff = [], [], [0]
+    for g in picks:
+        keep = rng.random(PER) < 0.8
+        shift = int(t[g * PER:(g + 1) * PER].min())
+        hh = h[g * PER:(g + 1) * PER][keep]; tt = (t[g * PER:(g + 1) * PER][keep] - shift).astype(np.uint32)
+        # plus decoys so that a window has several hundred hashes
+        dh = rng.integers(0, SPACE, 300, dtype=np.int64).astype(np.uint32); dt = rng.integers(0, 400, 300).astype(np.uint32)
+        hh = np.concatenate([hh, dh]); tt = np.concatenate([tt, dt])
+        o = np.argsort(tt, kind="stable")
+        qh.append(hh[o]); qt.append(tt[o]); qoff.append(qoff[-1] + len(hh))
+    QH, QT = np.concatenate(qh), np.concatenate(qt)
+
+    def check(index, tomb=None):
+        rows, n = eng.query_hashes(QH, QT, qoff)
+        for i in range(len(picks)):
+            rows_equal(rows[i], n[i], index.match(qh[i], qt[i], tombstone=tomb))
+        return rows, n
+
+    grouped, ng = check(ix)
+    st = eng.index_stats()
+    assert st["segments"] == 3 and st["segments_grouped"] == 2
+    assert {int(x) for x in grouped[0]["track"][:4]} == {5, 20000, 39000, 39001} and ng[0] >= 4
+    eng.index_set_grouping(False)
+    plain, npl = check(ix)
+    assert eng.index_stats()["segments_grouped"] == 0
+    assert np.array_equal(npl, ng) and all(np.array_equal(plain[i][:ng[i]], grouped[i][:ng[i]]) for i in range(len(picks)))
+    eng.index_set_grouping(True)
+
+    # delete inside a grouped segment and inside the partial one
+    assert eng.index_delete("20000") and eng.index_delete("39001")
+    tomb = np.zeros(NT, np.uint8); tomb[[20000, 39001]] = 1
+    rows, n = check(ix, tomb)
+    assert {int(x) for x in rows[0]["track"][:2]} == {5, 39000}
+
+    # later adds: the partial segment fills up and joins the group (3 members), a new partial one opens
+    h2, t2, off2 = _tiny_corpus(10000, PER, SPACE, 8)
+    h2[:PER] = h[5 * PER:6 * PER]; t2[:PER] = t[5 * PER:6 * PER]
+    assert eng.index_add_hashes(h2, t2, off2, [4000] * 10000, [f"x{g}" for g in range(10000)]).all()
+    H3 = np.concatenate([h, h2]); T3 = np.concatenate([t, t2])
+    TR3 = np.concatenate([track_of, np.repeat(np.arange(NT, NT + 10000, dtype=np.uint32), PER)])
+    ix3 = oracle.Index(H3, TR3, T3)
+    tomb3 = np.zeros(NT + 10000, np.uint8); tomb3[[20000, 39001]] = 1
+    rows, n = check(ix3, tomb3)
+    assert 40000 in rows[0]["track"][:3]
+    st = eng.index_stats()
+    assert st["segments"] == 4 and st["segments_grouped"] == 3
+
+    # persistence keeps the entries; the groups are derived data and come back on load
+    eng.index_save(str(tmp_path))
+    eng.index_clear()
+    eng.index_load(str(tmp_path))
+    assert eng.index_stats()["segments_grouped"] == 3
+    rows2, n2 = check(ix3, tomb3)
+    assert np.array_equal(n2, n) and all(np.array_equal(rows2[i][:n[i]], rows[i][:n[i]]) for i in range(len(picks)))

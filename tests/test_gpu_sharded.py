@@ -206,6 +206,25 @@ def test_fused_exchange_single_rank_and_timeout(engine):
                 assert np.array_equal(a[q, :nn[q]], b[q, :nn[q]])
         xa.close(); xb.close()
 
+    # the whole-step call on one rank equals the staged calls; a window too small for the fingerprints is reported
+    d_pcm = torch.from_numpy(qp).cuda()
+    xs = engine.exchange(0, 1, 16)
+    engine.identify_exchange_dev(xs, d_pcm.data_ptr(), qo, None, 0, rows, nrows)
+    engine.sync(); torch.cuda.synchronize()
+    xs.check()
+    assert np.array_equal(nrows.cpu().numpy(), nn)
+    a = rows.cpu().numpy()
+    for q in range(n):
+        assert np.array_equal(a[q, :nn[q]], b[q, :nn[q]])
+    xs.close()
+    tiny = engine.exchange(0, 1, 16, max_hashes_per_rank=8)
+    engine.identify_exchange_dev(tiny, d_pcm.data_ptr(), qo, None, 0, rows, nrows)
+    engine.sync()
+    with pytest.raises(EngineError) as ei:
+        tiny.check()
+    assert ei.value.status == -3 and (nrows.cpu().numpy() == 0).all()
+    tiny.close()
+
     x2 = engine.exchange(0, 2, 16)
     peer = engine.exchange(1, 2, 16)                   # exists, never publishes
     x2.connect_local([x2, peer]); peer.connect_local([x2, peer])
