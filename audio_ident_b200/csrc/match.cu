@@ -81,11 +81,12 @@ __device__ __forceinline__ void bitonic_sort_n(uint64_t* key, uint32_t* val, int
         }
 }
 
+constexpr int kOwnerCap = kSortN * 6;       // u16 entries that fit the sort buffers (skey + sval), which are idle during the vote loops
 struct MatchSmem {
-    uint32_t sketch[kSketch];
-    uint32_t tkey[kTable], tcnt[kTable], tmin[kTable], tmax[kTable];
+    alignas(16) uint32_t sketch[kSketch];
+    alignas(16) uint32_t tkey[kTable], tcnt[kTable], tmin[kTable], tmax[kTable];
     uint32_t qbeg[kQChunk], qadd[kQChunk], qstart[kQChunk + 1];
-    uint64_t skey[kSortN];
+    alignas(16) uint64_t skey[kSortN];     // skey + sval double as the vote -> hash map `owner` (u16[kOwnerCap])
     uint32_t sval[kSortN];
     uint64_t bkey[kBest];
     uint32_t bval[kBest];
@@ -116,11 +117,16 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
         if (dir) {
             const uint4 a = *reinterpret_cast<const uint4*>(dir + (size_t)h * 8);
             const uint32_t c67 = dir[(size_t)h * 8 + 4];
-            const uint32_t w[4] = {a.y, a.z, a.w, c67};
-            uint32_t at = a.x;
-            for (uint32_t j = 0; j < sub; j++) at += (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            uint32_t at = a.x, len = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)kGroupSegs; j++) {      // unrolled and predicated: the words stay in registers
+                const uint32_t word = j < 2 ? a.y : j < 4 ? a.z : j < 6 ? a.w : c67;
+                const uint32_t c = (word >> (16 * (j & 1))) & 0xffffu;
+                at += j < sub ? c : 0u;
+                len = j == sub ? c : len;
+            }
             lo = at;
-            return (w[sub >> 1] >> (16 * (sub & 1))) & 0xffffu;
+            return len;
         }
         lo = bucket[h];
         return bucket[h + 1] - lo;
@@ -192,18 +198,33 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     for (;;) {                                        // restarted with a finer partition if the exact table fills
         if (tid == 0) { sm.nbest = 0; sm.overflow = 0; }
         for (uint32_t r = 0; r < R; r++) {
-            if (!direct) for (int i = tid; i < kSketch; i += kThreads) sm.sketch[i] = 0;
-            for (int i = tid; i < kTable; i += kThreads) { sm.tkey[i] = kEmpty; sm.tcnt[i] = 0; sm.tmin[i] = 0xffffffffu; sm.tmax[i] = 0; }
+            if (!direct) for (int i = tid; i < kSketch / 4; i += kThreads) reinterpret_cast<uint4*>(sm.sketch)[i] = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < kTable / 4; i += kThreads) {
+                reinterpret_cast<uint4*>(sm.tkey)[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+                reinterpret_cast<uint4*>(sm.tcnt)[i] = make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4*>(sm.tmin)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                reinterpret_cast<uint4*>(sm.tmax)[i] = make_uint4(0, 0, 0, 0);
+            }
             if (tid == 0) { sm.used = 0; sm.hit = 0; }
             __syncthreads();
             for (int pass = direct ? 1 : 0; pass < 2; pass++) {
                 for (uint32_t c0 = 0; c0 < nh; c0 += kQChunk) {
                     const uint32_t nc = min((uint32_t)kQChunk, nh - c0);
                     const uint32_t nv = single ? total : stage(c0, nc);
+                    // vote v belongs to the hash i with qstart[i] <= v < qstart[i + 1]: one table lookup when the chunk's
+                    // votes fit the (idle) sort buffers, a binary search otherwise. The table is rebuilt per pass
+                    // because the top-k merge at the end of a round sorts in the same memory.
+                    uint16_t* owner = reinterpret_cast<uint16_t*>(sm.skey);
+                    const bool mapped = nv <= (uint32_t)kOwnerCap;
+                    if (mapped && (!single || pass == (direct ? 1 : 0))) {       // a single-chunk window keeps it for both passes
+                        for (uint32_t i = tid; i < nc; i += kThreads)
+                            for (uint32_t v = sm.qstart[i], ve = sm.qstart[i + 1]; v < ve; v++) owner[v] = (uint16_t)i;
+                        __syncthreads();
+                    }
                     for (uint32_t v = tid; v < nv; v += kThreads) {
-                        // largest i with qstart[i] <= v
-                        uint32_t lo = 0, hi = nc;
-                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; }
+                        uint32_t lo = 0;
+                        if (mapped) lo = owner[v];
+                        else { uint32_t hi = nc; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; } }
                         const uint32_t post = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
                         const uint32_t local = post >> AID_POST_T_BITS;
                         if (any_deleted && (seg.tomb[local >> 5] & (1u << (local & 31)))) continue;
