@@ -46,20 +46,34 @@ struct WarpSmem {
 
 // The window bins of (row, f) that lie outside the whole groups, tested exactly against v.
 // i = f & 15, g = f >> 4. Whole groups inside the window: g-2..g+2, plus g-3 if i <= 3, plus g+3 if i >= 12;
-// that leaves at most 15 bins on each side. All loads are issued before the first compare (one L2 round trip).
+// that leaves at most 15 bins on each side, and each side lies inside ONE aligned group (the left edge ends, the right
+// edge starts, at a group boundary). So the lane reads those two groups with 2 x 4 LDG.128 -- 16 B per lane and
+// instruction: one sector per row -- and masks the bins outside the window, instead of 30 scalar loads that each touch
+// a sector per row (the scalar version made the settlement two thirds of the kernel's L1 wavefronts). All loads are
+// issued before the first compare (one L2 round trip).
 __device__ __forceinline__ bool edges_le(const float* __restrict__ row, int f, float v) {
     const int i = f & 15, g = f >> 4;
-    const int left_lo = max(f - kHalfF, 0), left_hi = 16 * (i <= 3 ? g - 3 : g - 2) - 1;
-    const int right_lo = 16 * (i >= 12 ? g + 4 : g + 3), right_hi = min(f + kHalfF, AID_NBINS - 1);
-    float x[30];
+    const int gl = (i <= 3 ? g - 3 : g - 2) - 1;           // group holding the left edge bins (none if < 0)
+    const int gr = i >= 12 ? g + 4 : g + 3;                // group holding the right edge bins (none if > 31)
+    const int lo = f - kHalfF, hi = f + kHalfF;            // clipping at the row ends is implied by gl >= 0 / gr <= 31
+    float4 xl[4], xr[4];
+    const float4 none = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    const float4* pl = reinterpret_cast<const float4*>(row + 16 * max(gl, 0));
+    const float4* pr = reinterpret_cast<const float4*>(row + 16 * min(gr, 31));
 #pragma unroll
-    for (int k = 0; k < 15; k++) {
-        x[k] = left_lo + k <= left_hi ? __ldg(row + left_lo + k) : -1.0f;
-        x[15 + k] = right_lo + k <= right_hi ? __ldg(row + right_lo + k) : -1.0f;
+    for (int q = 0; q < 4; q++) {
+        xl[q] = gl >= 0 ? __ldg(pl + q) : none;
+        xr[q] = gr <= 31 ? __ldg(pr + q) : none;
     }
-    float m = x[0];
+    float m = -1.0f;
 #pragma unroll
-    for (int k = 1; k < 30; k++) m = fmaxf(m, x[k]);
+    for (int q = 0; q < 4; q++) {
+        const int bl = 16 * gl + 4 * q, br = 16 * gr + 4 * q;
+        m = fmaxf(m, bl + 0 >= lo ? xl[q].x : -1.0f); m = fmaxf(m, bl + 1 >= lo ? xl[q].y : -1.0f);
+        m = fmaxf(m, bl + 2 >= lo ? xl[q].z : -1.0f); m = fmaxf(m, bl + 3 >= lo ? xl[q].w : -1.0f);
+        m = fmaxf(m, br + 0 <= hi ? xr[q].x : -1.0f); m = fmaxf(m, br + 1 <= hi ? xr[q].y : -1.0f);
+        m = fmaxf(m, br + 2 <= hi ? xr[q].z : -1.0f); m = fmaxf(m, br + 3 <= hi ? xr[q].w : -1.0f);
+    }
     return m <= v;
 }
 
