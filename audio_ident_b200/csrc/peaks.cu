@@ -13,7 +13,8 @@
 //    sign of A    = set if A passes the gate and A == C5 ("candidate group": a point can only be the maximum of
 //                   its 103-bin window if it is the maximum of such a group, because groups g-2..g+2 lie inside
 //                   every window of group g)
-//  * Row pass: 4 x LDG.128 per lane (the next row is already in flight), one max-reduction, four shuffles.
+//  * Row pass: 4 x LDG.128 per lane, each instruction 512 contiguous bytes (the next two rows are already in flight),
+//    a 4 x 4 transpose-reduce inside every quad of lanes and one shuffle to hand group g to lane g, four shuffles for C5.
 //  * Column pass, 12 rows behind: the maximum of a lane's C5 column over the 25 rows of the window comes from the
 //    van Herk / Gil-Werman decomposition -- a running prefix maximum over the current block of 25 rows (one
 //    register) and suffix maxima of the previous block (written over the C5 ring once per block): one shared
@@ -83,6 +84,16 @@ __device__ __forceinline__ void load_row(float4 (&x)[4], const float* __restrict
     for (int q = 0; q < 4; q++) x[q] = __ldg(s + q);
 }
 
+// Streaming form of the row load: instruction q reads float4 number 32 q + lane, so a warp instruction covers 512
+// contiguous bytes (4 lines, 16 sectors) instead of 32 chunks 64 B apart (16 lines, every sector touched by two
+// instructions). The lane then holds four float4 of four different groups: group 8 q + j sits in lanes 4 j .. 4 j + 3 of
+// instruction q.
+__device__ __forceinline__ void load_row_stream(float4 (&x)[4], const float* __restrict__ srow, int lane) {
+    const float4* s = reinterpret_cast<const float4*>(srow) + lane;
+#pragma unroll
+    for (int q = 0; q < 4; q++) x[q] = __ldg(s + 32 * q);
+}
+
 struct Stream {             // per-warp state (the same in every lane except px)
     const float* base;      // row 0 of the track
     uint32_t* out;          // the unit's slot list in global memory
@@ -97,12 +108,22 @@ struct Stream {             // per-warp state (the same in every lane except px)
     float px;               // per lane: max of C5 over those rows
 };
 
-// Row pass, register part: group maximum A and 5-group maximum C5 of one row. Pure register/shuffle code, so
-// the two rows of a trip can be interleaved by the scheduler.
-__device__ __forceinline__ void row_reduce(const float4 (&x)[4], float& A, float& c5) {
-    A = fmaxf(fmaxf(x[0].x, x[0].y), fmaxf(x[0].z, x[0].w));
+// Row pass, register part: group maximum A and 5-group maximum C5 of one row loaded by load_row_stream. Pure
+// register/shuffle code, so the two rows of a trip can be interleaved by the scheduler. The four partial maxima of a
+// lane belong to four groups; a 4 x 4 transpose-reduce inside each quad of lanes (3 shuffles) leaves lane 4 j + p with
+// the maximum of group 8 q(p) + j, q(p) = 2 (p & 1) + (p >> 1), and one more shuffle hands group g to lane g.
+__device__ __forceinline__ void row_reduce(const float4 (&x)[4], float& A, float& c5, int lane) {
+    float a[4];
 #pragma unroll
-    for (int q = 1; q < 4; q++) A = fmaxf(A, fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w)));
+    for (int q = 0; q < 4; q++) a[q] = fmaxf(fmaxf(x[q].x, x[q].y), fmaxf(x[q].z, x[q].w));
+    const bool odd = lane & 1, hi = lane & 2;
+    const float r1 = __shfl_xor_sync(AID_FULL_MASK, odd ? a[0] : a[2], 1);
+    const float r2 = __shfl_xor_sync(AID_FULL_MASK, odd ? a[1] : a[3], 1);
+    const float b0 = fmaxf(odd ? a[2] : a[0], r1), b1 = fmaxf(odd ? a[3] : a[1], r2);
+    const float r3 = __shfl_xor_sync(AID_FULL_MASK, hi ? b0 : b1, 2);
+    const float c = fmaxf(hi ? b1 : b0, r3);
+    const int q = lane >> 3;                                 // this lane's group is 8 q + (lane & 7)
+    A = __shfl_sync(AID_FULL_MASK, c, 4 * (lane & 7) + ((q >> 1) | ((q & 1) << 1)));
     // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
     const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
     const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
@@ -265,18 +286,18 @@ k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
 
     // two rows per trip, the next two already in flight
     float4 na[4], nb[4];
-    load_row(na, st.base + (int64_t)st.lo * AID_NBINS, lane);
-    load_row(nb, st.base + (int64_t)min(st.lo + 1, st.hi - 1) * AID_NBINS, lane);
+    load_row_stream(na, st.base + (int64_t)st.lo * AID_NBINS, lane);
+    load_row_stream(nb, st.base + (int64_t)min(st.lo + 1, st.hi - 1) * AID_NBINS, lane);
     for (int r = st.lo; r < st.hi; r += 2) {
         const float4 xa[4] = {na[0], na[1], na[2], na[3]};
         const float4 xb[4] = {nb[0], nb[1], nb[2], nb[3]};
         if (r + 2 < st.hi) {
-            load_row(na, st.base + (int64_t)(r + 2) * AID_NBINS, lane);
-            load_row(nb, st.base + (int64_t)min(r + 3, st.hi - 1) * AID_NBINS, lane);
+            load_row_stream(na, st.base + (int64_t)(r + 2) * AID_NBINS, lane);
+            load_row_stream(nb, st.base + (int64_t)min(r + 3, st.hi - 1) * AID_NBINS, lane);
         }
         float A0, c0, A1, c1;
-        row_reduce(xa, A0, c0);
-        row_reduce(xb, A1, c1);
+        row_reduce(xa, A0, c0, lane);
+        row_reduce(xb, A1, c1, lane);
         row_commit(sm, st, A0, c0, r, lane);
         if (r - kHalfT >= st.row0) verify_row(sm, st, r - kHalfT, r, lane);
         if (r + 1 < st.hi) {
