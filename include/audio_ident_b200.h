@@ -189,6 +189,8 @@ typedef struct aid_exchange aid_exchange;
  * (0 = 1024 per window of a rank's slice; a 3.5 s window yields about 300) */
 int  aid_exchange_create(aid_engine* e, int rank, int world, int max_queries, int64_t max_hashes_per_rank,
                          aid_exchange** out);
+/* waits for the device, unmaps the peers' windows and frees this rank's; call it before aid_engine_destroy of its engine
+ * and only after every rank has finished its last exchange call (peers may still be storing into the window) */
 void aid_exchange_destroy(aid_exchange* x);
 /* handle[64] of this rank's window for ranks in other processes (a cudaIpcMemHandle_t) */
 int  aid_exchange_handle(aid_exchange* x, uint8_t* handle);
