@@ -31,7 +31,8 @@ constexpr int kSketch = 2048;
 constexpr int kTable = 256;
 constexpr int kTableMaxLoad = 192;
 constexpr int kQChunk = 512;
-constexpr int kVotesPerRound = 1024;
+constexpr int kVotesPerRound = 2048;       // = kSketch: ~1 vote per counter keeps chance counts >= AID_MIN_VOTES at ~1 per round; a (window, segment) CTA
+                                            // sees ~1,000 votes, so the usual CTA needs one round, not two (each round reads every posting twice)
 constexpr int kBest = 64;                 // >= AID_MAX_ROWS, power of two
 constexpr int kSortN = 512;               // kTable + kBest <= kSortN
 constexpr uint32_t kEmpty = 0xffffffffu;
