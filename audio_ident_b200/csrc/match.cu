@@ -92,7 +92,7 @@ struct MatchSmem {
     uint64_t bkey[kBest];
     uint32_t bval[kBest];
     uint32_t wsum[kThreads / 32];
-    uint32_t total, used, overflow, nbest, hit;
+    uint32_t total, used, overflow, nbest, hit, maybe;
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -206,9 +206,12 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
                 reinterpret_cast<uint4*>(sm.tmin)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
                 reinterpret_cast<uint4*>(sm.tmax)[i] = make_uint4(0, 0, 0, 0);
             }
-            if (tid == 0) { sm.used = 0; sm.hit = 0; }
+            if (tid == 0) { sm.used = 0; sm.hit = 0; sm.maybe = 0; }
             __syncthreads();
             for (int pass = direct ? 1 : 0; pass < 2; pass++) {
+                // no counter of the sketch reached AID_MIN_VOTES: no key can have, and the second pass over the postings
+                // is skipped (the usual case: one segment in 62 holds the track a window comes from)
+                if (pass == 1 && !direct && !sm.maybe) break;
                 for (uint32_t c0 = 0; c0 < nh; c0 += kQChunk) {
                     const uint32_t nc = min((uint32_t)kQChunk, nh - c0);
                     const uint32_t nv = single ? total : stage(c0, nc);
@@ -233,7 +236,7 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
                         const uint32_t m = mix32(key);
                         if (R > 1 && (m >> 12) % R != r) continue;
                         const uint32_t idx = m & (kSketch - 1);
-                        if (pass == 0) { atomicAdd(&sm.sketch[idx], 1u); continue; }
+                        if (pass == 0) { if (atomicAdd(&sm.sketch[idx], 1u) + 1 == AID_MIN_VOTES) sm.maybe = 1; continue; }
                         if (!direct && sm.sketch[idx] < AID_MIN_VOTES) continue;
                         const uint32_t tq = AID_QUERY_MAX_FRAMES - sm.qadd[lo];
                         uint32_t slot = (m >> 20) & (kTable - 1);
