@@ -13,6 +13,8 @@
 // per-bucket cursors -> per-bucket sort (buckets hold a handful of postings). Only the last segment is open;
 // adding tracks marks it dirty and the next query (or aid_index_commit) rebuilds just that segment.
 // Deleting a track sets a tombstone bit that the matcher checks; its postings stay until the segment is rebuilt.
+// Full segments give up their own table and share a hash directory eight at a time (index.h SegGroup; build_group
+// below): the matcher's eight CTAs of a window then read the same directory sector per hash and adjacent posting runs.
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>

@@ -6,20 +6,22 @@
 // bit-exact rows (count, track, offset, q_first, q_last) in the same order.
 //
 // k_match: one CTA per (query window, index segment).
-//   0. stage the query's hashes: bucket begin / length per hash, prefix sum of the lengths -> a flat list of
-//      votes, so every thread handles the same number of postings whatever the bucket sizes are;
+//   0. stage the query's hashes: run begin / length per hash (from the segment's own table or from the directory it
+//      shares with up to seven sibling segments, index.h SegGroup), prefix sum of the lengths -> a flat list of votes,
+//      so every thread handles the same number of postings whatever the bucket sizes are; a u16 vote -> hash map in
+//      the idle sort buffers saves a binary search per vote;
 //   1. pass 1 adds every vote key (local_track << 18 | t_ref - t_query + bias: one integer add on the posting)
-//      into a 2048-counter shared-memory sketch with atomics;
-//   2. pass 2 re-reads the postings (now in L2) and inserts only keys whose sketch counter reached
-//      AID_MIN_VOTES into an exact shared-memory hash table (atomicCAS on the key, atomicAdd on the count,
-//      atomicMin/Max on the query time);
+//      into a 2048-counter shared-memory sketch with atomics (a CTA sees ~1,000 votes; <= 192 go straight to 2.);
+//   2. pass 2 -- skipped when no counter reached AID_MIN_VOTES, which is the usual case -- re-reads the postings
+//      (now in L1/L2) and inserts only keys whose sketch counter reached AID_MIN_VOTES into an exact shared-memory
+//      hash table (atomicCAS on the key, atomicAdd on the count, atomicMin/Max on the query time);
 //   3. exact counts >= AID_MIN_VOTES are merged into the CTA's running top-50 with a bitonic network.
 //   Windows with more votes than the sketch can filter are processed in R rounds over a hash partition of
 //   the keys; if the exact table still fills up the CTA doubles R and starts over. Exactness never depends on
 //   the sketch: it only rejects keys that cannot reach the threshold.
 // k_rank: one CTA per query merges the per-segment top-50 lists (a track lives in exactly one segment, so no
 //   partial counts ever need adding) and writes the final rows.
-// HBM traffic per query window: 8 B of bucket table per hash and 4 B per posting touched, random access.
+// HBM traffic per query window: one table / directory entry per hash and 4 B per posting touched, random access.
 #include <algorithm>
 #include "engine.h"
 #include "index.h"
