@@ -140,3 +140,59 @@ def test_batch_entry_equals_single(oracle):
     for i, c in enumerate(clips):
         a, b = oracle.fingerprint(c)
         assert np.array_equal(h[hoff[i]:hoff[i + 1]], a) and np.array_equal(t[hoff[i]:hoff[i + 1]], b)
+
+
+# ---------------------------------------------------------------- properties of the domain (size-independent)
+def test_hop_aligned_excerpt_keeps_hashes_and_shifts_time(oracle):
+    """An excerpt that starts on a hop boundary sees the same frames as the track, so every landmark whose peaks'
+    neighbourhoods lie inside the excerpt reappears with the same hash and t shifted by the start frame."""
+    x = synth.make_track(3, 12.0)
+    k = 173                                                   # start frame
+    h, t = oracle.fingerprint(x)
+    he, te = oracle.fingerprint(x[k * 128:k * 128 + 6 * 16000])
+    full = {(int(a), int(b)) for a, b in zip(h, t)}
+    inside = [(int(a), int(b) + k) for a, b in zip(he, te) if 13 <= int(b) < oracle.num_frames(6 * 16000) - 13 - 33 - 12]
+    assert len(inside) > 50
+    assert sum(p in full for p in inside) >= 0.95 * len(inside)   # the rest: fan-out truncated differently at the cut
+
+
+def test_self_identification_offset_is_the_start_frame(oracle):
+    tracks = [synth.make_track(40 + k, 15.0) for k in range(6)]
+    fps = [oracle.fingerprint(x) for x in tracks]
+    H = np.concatenate([h for h, _ in fps]); T = np.concatenate([t for _, t in fps])
+    TR = np.concatenate([np.full(len(h), k, np.uint32) for k, (h, _) in enumerate(fps)])
+    ix = oracle.Index(H, TR, T)
+    for k, start in ((0, 0), (2, 37), (5, 611)):
+        q = tracks[k][start * 128:start * 128 + int(3.5 * 16000)]
+        rows = ix.match(*oracle.fingerprint(q))
+        assert len(rows) >= 1 and rows["track"][0] == k and rows["offset"][0] == start
+        assert rows["count"][0] >= 20 and np.all(np.diff(rows["count"].astype(np.int64)) <= 0)
+        assert rows["q_first"][0] <= rows["q_last"][0] < oracle.num_frames(len(q))
+
+
+@pytest.mark.parametrize("n", [0, 1, 1023, 1024, 1151, 1152])
+def test_short_inputs(oracle, n):
+    """Fewer than 1024 samples give no frame; 1024..1151 give one; no padding anywhere."""
+    x = np.linspace(-0.5, 0.5, n, dtype=np.float32)
+    frames = oracle.num_frames(n)
+    assert frames == (0 if n < 1024 else (n - 1024) // 128 + 1)
+    h, t = oracle.fingerprint(x)
+    assert len(h) == 0 and len(t) == 0
+    if frames:
+        assert oracle.stft(x).shape == (frames, 512)
+
+
+def test_deleted_track_disappears_and_only_it(oracle):
+    tracks = [synth.make_track(60 + k, 10.0) for k in range(4)]
+    tracks.append(tracks[1].copy())
+    fps = [oracle.fingerprint(x) for x in tracks]
+    H = np.concatenate([h for h, _ in fps]); T = np.concatenate([t for _, t in fps])
+    TR = np.concatenate([np.full(len(h), k, np.uint32) for k, (h, _) in enumerate(fps)])
+    ix = oracle.Index(H, TR, T)
+    q = oracle.fingerprint(tracks[1][16000:16000 + 56000])
+    both = ix.match(*q)
+    assert [int(x) for x in both["track"][:2]] == [1, 4] and both["count"][0] == both["count"][1]
+    tomb = np.zeros(5, np.uint8); tomb[1] = 1
+    one = ix.match(*q, tombstone=tomb)
+    assert int(one["track"][0]) == 4 and 1 not in one["track"]
+    assert np.array_equal(one, both[both["track"] != 1])
