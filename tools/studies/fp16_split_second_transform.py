@@ -56,6 +56,10 @@ def real_gemm(a: np.ndarray, b: np.ndarray, mode: str) -> np.ndarray:
         ah, al = split16(a); bh, bl = split16(b)
         s = np.float32(1.0 / 2048.0)
         return (ah @ bh + (ah @ bl) * s + (al @ bh) * s).astype(np.float32)
+    if mode == "fp16x3u":            # the same without scaling lo: small lo parts fall into FP16 subnormals (absolute step 6e-8),
+        ah = a.astype(np.float16).astype(np.float32); al = (a - ah).astype(np.float16).astype(np.float32)   # which is what three
+        bh = b.astype(np.float16).astype(np.float32); bl = (b - bh).astype(np.float16).astype(np.float32)   # MMAs into one accumulator see
+        return (ah @ bh + ah @ bl + al @ bh).astype(np.float32)
     return (round_to(a, mode) @ round_to(b, mode)).astype(np.float32)
 
 
@@ -75,9 +79,32 @@ def second_transform(Y: np.ndarray, mode: str) -> np.ndarray:
     return Z
 
 
+def both_transforms(zz: np.ndarray, mode: str) -> np.ndarray:
+    """zz [P, n2, n1] complex64 -> Z [1024, P]: BOTH 32-point transforms as products with the one constant matrix W_32
+    (64 x 64 as a real matrix), the inter-transform twiddle W_1024^(n1 k1) applied elementwise in FP32 in between."""
+    P = zz.shape[0]
+    W = np.exp(-2j * np.pi * np.outer(np.arange(32), np.arange(32)) / 32)
+    Wr, Wi = W.real.astype(np.float32), W.imag.astype(np.float32)
+    # first: Y[k1, (n1, p)] = sum_n2 W[k1, n2] z[n2, (n1, p)]
+    d = np.ascontiguousarray(np.transpose(zz, (1, 2, 0))).reshape(32, 32 * P)         # [n2, n1 * P]
+    dr, di = np.ascontiguousarray(d.real), np.ascontiguousarray(d.imag)
+    yr = real_gemm(Wr, dr, mode) - real_gemm(Wi, di, mode)
+    yi = real_gemm(Wr, di, mode) + real_gemm(Wi, dr, mode)
+    Y = (yr + 1j * yi).astype(np.complex64).reshape(32, 32, P)                        # [k1, n1, p]
+    tw = np.exp(-2j * np.pi * np.outer(np.arange(32), np.arange(32)) / N).astype(np.complex64)   # [k1, n1]
+    Y = (Y * tw[:, :, None]).astype(np.complex64)
+    # second: Z[k1 + 32 k2, p] = sum_n1 W[k2, n1] Y[k1, n1, p]
+    e = np.ascontiguousarray(np.transpose(Y, (1, 0, 2))).reshape(32, 32 * P)           # [n1, k1 * P]
+    er, ei = np.ascontiguousarray(e.real), np.ascontiguousarray(e.imag)
+    zr = real_gemm(Wr, er, mode) - real_gemm(Wi, ei, mode)
+    zi = real_gemm(Wr, ei, mode) + real_gemm(Wi, er, mode)
+    Zk = (zr + 1j * zi).astype(np.complex64).reshape(32, 32, P)                       # [k2, k1, p]
+    return Zk.reshape(N, P)                                                           # k = k1 + 32 k2
+
+
 def study(n_tracks: int, seconds: float) -> None:
     w = window()
-    modes = ["fp32", "fp16x3", "tf32", "fp16", "bf16"]
+    modes = ["fp32", "fp16x3", "tf32", "fp16", "bf16", "both:fp16x3", "both:fp16x3u", "both:tf32"]
     worst = {m: 0.0 for m in modes}
     bad = {m: 0 for m in modes}
     total = 0
@@ -96,7 +123,7 @@ def study(n_tracks: int, seconds: float) -> None:
         Y = np.fft.fft(zz.astype(np.complex128), axis=1).astype(np.complex64)   # [P, k1, n1]
         Y = np.ascontiguousarray(np.transpose(Y, (2, 1, 0)))      # [n1, k1, P]
         for m in modes:
-            Z = second_transform(Y, m).T                          # [P, 1024]
+            Z = (both_transforms(zz, m[5:]) if m.startswith("both:") else second_transform(Y, m)).T   # [P, 1024]
             Zm = np.conj(np.roll(Z[:, ::-1], 1, axis=1))          # conj(Z[N - k])
             Xa = (Z + Zm)[:, :512]
             Xb = (-1j * (Z - Zm))[:, :512]
@@ -109,7 +136,8 @@ def study(n_tracks: int, seconds: float) -> None:
         total += T * 512
     print(f"{n_tracks} tracks x {seconds:g} s = {total} stored values; tolerance {TOL:g} * max(|S|, 1)")
     for m in modes:
-        print(f"  second transform in {m:7s}: worst scaled error {worst[m]:.3g}, values out of tolerance {bad[m]}")
+        what = "both transforms in " + m[5:] if m.startswith("both:") else "second transform in " + m
+        print(f"  {what:28s}: worst scaled error {worst[m]:.3g}, values out of tolerance {bad[m]}")
 
 
 if __name__ == "__main__":
