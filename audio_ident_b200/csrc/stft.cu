@@ -304,12 +304,27 @@ k_stft(const float* __restrict__ window, const float* __restrict__ twist,
     }
 }
 
+#ifdef AID_STFT_TC
+#include "../../tools/microbench/stft_tc.cuh"      // experimental tensor-core second transform (micro-benchmarks only)
+#endif
+
 }  // namespace
 
 cudaError_t aid_launch_stft(const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
                             int n_units, float* d_spec, cudaStream_t st) {
     if (n_units <= 0) return cudaSuccess;
+#ifdef AID_STFT_TC
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t ce = cudaFuncSetAttribute(k_stft_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftTcSmem) + 1024);
+        if (ce != cudaSuccess) return ce;
+        configured = true;
+    }
+    k_stft_tc<<<(n_units + 3) / 4, 128, sizeof(StftTcSmem) + 1024, st>>>(tb.window, tb.twist, d_pcm, d_units, n_units, d_spec);
+    return cudaGetLastError();
+#else
     const int grid = (n_units + kWarpsPerCta - 1) / kWarpsPerCta;
     k_stft<<<grid, kWarpsPerCta * 32, 0, st>>>(tb.window, tb.twist, d_pcm, d_units, n_units, d_spec);
     return cudaGetLastError();
+#endif
 }
