@@ -9,8 +9,12 @@
 // With `x3` it runs the split product the STFT needs (hi*hi + hi*lo + lo*hi into one accumulator) on FP32 inputs and
 // reports the error against a double-precision product.
 //
+// With `hankel` (not yet run) it asks whether a descriptor may describe OVERLAPPING rows: A[m][k] = s[8 m + k] read straight
+// from a contiguous FP16 array (leading-dimension offset 16 B = the next 8 halves, core-matrix rows 16 B apart), which is
+// what a tensor-core STFT fed with raw samples instead of per-frame operand tiles would need.
+//
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o bin/umma_probe umma_probe.cu
-// Run:   ./bin/umma_probe [x3]
+// Run:   ./bin/umma_probe [x3 | hankel]
 // Status: run on a B200 at the end of round 1 (gpurun): "PASS: 0 of 8192 entries off, worst absolute error 0 (exact
 // small integers)" and "PASS: 0 of 8192 entries off, worst absolute error 0.00015 (FP16 hi+lo split, 3 products ...)" --
 // i.e. the descriptors, the layout and the TMEM read-back below are right, and three MMAs into one accumulator give
@@ -48,7 +52,7 @@ __device__ inline uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) 
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 
 __global__ void __launch_bounds__(128, 1)
-k_probe(const __half* __restrict__ A, const __half* __restrict__ B, int n_terms, float* __restrict__ D) {
+k_probe(const __half* __restrict__ A, const __half* __restrict__ B, int n_terms, int hankel, float* __restrict__ D) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                           // n_terms x A_BYTES
     unsigned char* sB = smem + 3 * A_BYTES;             // n_terms x B_BYTES
@@ -57,6 +61,9 @@ k_probe(const __half* __restrict__ A, const __half* __restrict__ B, int n_terms,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     for (int t = 0; t < n_terms; t++) {
+        if (hankel) {                                   // the 1-D sequence itself; rows will overlap
+            for (int i = tid; i < 8 * (M - 1) + K; i += blockDim.x) reinterpret_cast<__half*>(sA)[i] = A[i];
+        } else
         for (int i = tid; i < M * K; i += blockDim.x)
             *reinterpret_cast<__half*>(sA + t * A_BYTES + a_off(i / K, i % K)) = A[(size_t)t * M * K + i];
         for (int i = tid; i < N * K; i += blockDim.x)
@@ -84,7 +91,8 @@ k_probe(const __half* __restrict__ A, const __half* __restrict__ B, int n_terms,
         bool first = true;
         for (int p = 0; p < n_prod; p++)
             for (int ks = 0; ks < K / UMMA_K; ks++) {
-                const uint64_t da = smem_desc(smem_u32(sA + pa[p] * A_BYTES) + ks * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t da = hankel ? smem_desc(smem_u32(sA) + ks * 32, 16, SBO)      // K step of 16 halves = 32 B
+                                           : smem_desc(smem_u32(sA + pa[p] * A_BYTES) + ks * 2 * LBO_A, LBO_A, SBO);
                 const uint64_t db = smem_desc(smem_u32(sB + pb[p] * B_BYTES) + ks * 2 * LBO_B, LBO_B, SBO);
                 const uint32_t acc = first ? 0u : 1u;
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -126,10 +134,16 @@ k_probe(const __half* __restrict__ A, const __half* __restrict__ B, int n_terms,
 
 int main(int argc, char** argv) {
     const bool split = argc > 1 && argv[1][0] == 'x';
+    const bool hankel = argc > 1 && argv[1][0] == 'h';
     const int n_terms = split ? 2 : 1;
     std::vector<double> a(M * K), b(N * K);
     srand(7);
     for (auto& v : a) v = split ? (rand() / (double)RAND_MAX * 2.0 - 1.0) : (double)(rand() % 9 - 4);      // exact small integers, or reals in [-1, 1]
+    std::vector<double> seq(8 * (M - 1) + K);
+    if (hankel) {                                           // a[m][k] = seq[8 m + k]
+        for (auto& v : seq) v = (double)(rand() % 9 - 4);
+        for (int m = 0; m < M; m++) for (int k = 0; k < K; k++) a[m * K + k] = seq[8 * m + k];
+    }
     for (auto& v : b) v = split ? (rand() / (double)RAND_MAX * 60.0 - 30.0) : (double)(rand() % 9 - 4);
     std::vector<__half> ha((size_t)n_terms * M * K), hb((size_t)n_terms * N * K);
     for (int i = 0; i < M * K; i++) {
@@ -149,7 +163,11 @@ int main(int argc, char** argv) {
     CK(cudaMemset(dD, 0xff, M * N * 4));
     const size_t smem = 3 * A_BYTES + 3 * B_BYTES + 64;
     CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_probe<<<1, 128, smem>>>(dA, dB, n_terms, dD);
+    if (hankel) {                                           // the device gets the sequence, not the matrix
+        for (size_t j = 0; j < seq.size(); j++) ha[j] = __float2half((float)seq[j]);
+        CK(cudaMemcpy(dA, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+    }
+    k_probe<<<1, 128, smem>>>(dA, dB, n_terms, hankel ? 1 : 0, dD);
     CK(cudaDeviceSynchronize());
     std::vector<float> d(M * N);
     CK(cudaMemcpy(d.data(), dD, M * N * 4, cudaMemcpyDeviceToHost));
@@ -163,6 +181,6 @@ int main(int argc, char** argv) {
             if (err > (split ? 1e-3 : 0.0)) { if (bad < 8) printf("  D[%d][%d] = %g, expected %g\n", m, n, d[m * N + n], ref); bad++; }
         }
     printf("%s: %d of %d entries off, worst absolute error %.3g (%s)\n", bad ? "FAIL" : "PASS", bad, M * N, worst,
-           split ? "FP16 hi+lo split, 3 products, |A| <= 1, |B| <= 30, K = 64" : "exact small integers");
+           split ? "FP16 hi+lo split, 3 products, |A| <= 1, |B| <= 30, K = 64" : hankel ? "overlapping rows A[m][k] = s[8 m + k]" : "exact small integers");
     return bad ? 2 : 0;
 }
