@@ -102,9 +102,35 @@ def both_transforms(zz: np.ndarray, mode: str) -> np.ndarray:
     return Zk.reshape(N, P)                                                           # k = k1 + 32 k2
 
 
+def raw_sample_transforms(x: np.ndarray, T: int, w: np.ndarray, mode: str) -> np.ndarray:
+    """The sliding-operand variant: the window is folded into 32 first-stage matrices
+    G_n1[k1][n2] = w[n1 + 32 n2] W_32^(n2 k1) and the data operand is the RAW sample sequence (split into FP16 hi + lo once
+    per sample, not per frame). Returns Z [1024, T / 2] for the packed frame pairs, second stage as in both_transforms."""
+    n2 = np.arange(32)
+    Y = np.empty((T, 32, 32), np.complex64)                                   # [t, k1, n1]
+    for n1 in range(32):
+        G = (w[n1 + 32 * n2].astype(np.float64)[None, :] * np.exp(-2j * np.pi * np.outer(np.arange(32), n2) / 32))   # [k1, n2]
+        Gr, Gi = G.real.astype(np.float32), G.imag.astype(np.float32)
+        seq = x[n1::32]                                                       # x[n1 + 32 j]
+        idx = n2[:, None] + 4 * np.arange(T)[None, :]                         # j = n2 + 4 t
+        d = np.ascontiguousarray(seq[idx]).astype(np.float32)                 # [n2, t]  (the Hankel operand)
+        Y[:, :, n1] = (real_gemm(Gr, d, mode) + 1j * real_gemm(Gi, d, mode)).T.astype(np.complex64)
+    z = (0.5 * (Y[0::2] + 1j * Y[1::2])).astype(np.complex64)                 # pack frame pairs: [P, k1, n1]
+    P = z.shape[0]
+    tw = np.exp(-2j * np.pi * np.outer(np.arange(32), np.arange(32)) / N).astype(np.complex64)
+    z = (z * tw[None, :, :]).astype(np.complex64)
+    W = np.exp(-2j * np.pi * np.outer(np.arange(32), np.arange(32)) / 32)
+    Wr, Wi = W.real.astype(np.float32), W.imag.astype(np.float32)
+    e = np.ascontiguousarray(np.transpose(z, (2, 1, 0))).reshape(32, 32 * P)   # [n1, k1 * P]
+    er, ei = np.ascontiguousarray(e.real), np.ascontiguousarray(e.imag)
+    zr = real_gemm(Wr, er, mode) - real_gemm(Wi, ei, mode)
+    zi = real_gemm(Wr, ei, mode) + real_gemm(Wi, er, mode)
+    return (zr + 1j * zi).astype(np.complex64).reshape(32, 32, P).reshape(N, P)
+
+
 def study(n_tracks: int, seconds: float) -> None:
     w = window()
-    modes = ["fp32", "fp16x3", "tf32", "fp16", "bf16", "both:fp16x3", "both:fp16x3u", "both:tf32"]
+    modes = ["fp32", "fp16x3", "tf32", "fp16", "bf16", "both:fp16x3", "both:fp16x3u", "both:tf32", "raw:fp16x3u", "raw:fp32"]
     worst = {m: 0.0 for m in modes}
     bad = {m: 0 for m in modes}
     total = 0
@@ -123,7 +149,10 @@ def study(n_tracks: int, seconds: float) -> None:
         Y = np.fft.fft(zz.astype(np.complex128), axis=1).astype(np.complex64)   # [P, k1, n1]
         Y = np.ascontiguousarray(np.transpose(Y, (2, 1, 0)))      # [n1, k1, P]
         for m in modes:
-            Z = (both_transforms(zz, m[5:]) if m.startswith("both:") else second_transform(Y, m)).T   # [P, 1024]
+            if m.startswith("raw:"):
+                Z = raw_sample_transforms(x, T, w, m[4:]).T
+            else:
+                Z = (both_transforms(zz, m[5:]) if m.startswith("both:") else second_transform(Y, m)).T   # [P, 1024]
             Zm = np.conj(np.roll(Z[:, ::-1], 1, axis=1))          # conj(Z[N - k])
             Xa = (Z + Zm)[:, :512]
             Xb = (-1j * (Z - Zm))[:, :512]
@@ -136,8 +165,9 @@ def study(n_tracks: int, seconds: float) -> None:
         total += T * 512
     print(f"{n_tracks} tracks x {seconds:g} s = {total} stored values; tolerance {TOL:g} * max(|S|, 1)")
     for m in modes:
-        what = "both transforms in " + m[5:] if m.startswith("both:") else "second transform in " + m
-        print(f"  {what:28s}: worst scaled error {worst[m]:.3g}, values out of tolerance {bad[m]}")
+        what = ("both transforms in " + m[5:] if m.startswith("both:") else
+                "raw samples x window-folded matrices, " + m[4:] if m.startswith("raw:") else "second transform in " + m)
+        print(f"  {what:52s}: worst scaled error {worst[m]:.3g}, values out of tolerance {bad[m]}")
 
 
 if __name__ == "__main__":
