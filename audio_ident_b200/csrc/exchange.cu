@@ -103,6 +103,8 @@ k_publish_hashes(const uint32_t* __restrict__ hash, const uint32_t* __restrict__
 }
 
 // one warp holds the stream until every rank's fingerprints of this epoch are in this rank's window
+// (err[0] = timeout seen, err[1] = a slice did not fit: both sticky until aid_exchange_status reports and clears them;
+// while err[0] is set k_match probes nothing -- the hash window is only partly written -- and the merge reports -1 rows)
 __global__ void k_wait_hashes(unsigned char* window, int world, uint32_t epoch, uint32_t* err, long long timeout_cycles) {
     const int lane = threadIdx.x;
     if (lane >= world) return;
@@ -124,8 +126,8 @@ k_merge_blocks(unsigned char* __restrict__ window, const XchgLayout lay, uint32_
     if (q >= n_q) return;
 
     // every rank's block of this epoch has to be complete: lane p watches the flag rank p publishes
-    bool ok = true;
-    if (lane < world) {
+    bool ok = *reinterpret_cast<volatile uint32_t*>(err) == 0;     // an earlier wait of this exchange already gave up
+    if (ok && lane < world) {
         ok = wait_flag(XchgLayout::row_flag(window) + lane, epoch, timeout_cycles);
     }
     if (!__all_sync(AID_FULL_MASK, ok)) {                    // a peer never delivered: report, do not invent rows
@@ -273,7 +275,9 @@ extern "C" int aid_exchange_status(aid_exchange* x) {
     if (!x) return AID_E_ARG;
     X_CUDA(x, cudaSetDevice(x->e->device));
     uint32_t err[2] = {0, 0};
+    X_CUDA(x, cudaDeviceSynchronize());            // the engine's streams are non-blocking: a plain cudaMemcpy would not wait for them
     X_CUDA(x, cudaMemcpy(err, x->d_done + 1, 8, cudaMemcpyDeviceToHost));
+    if (err[0] || err[1]) X_CUDA(x, cudaMemset(x->d_done + 1, 0, 8));      // reported once: a transient failure must not fail every later step
     if (err[0]) {
         x->e->err = "a peer rank did not deliver its block within the exchange timeout";
         return AID_E_TIMEOUT;
@@ -295,7 +299,8 @@ static int match_and_merge(aid_engine* e, aid_exchange* x, uint32_t epoch, const
     for (int p = 0; p < x->world; p++) sink.window[p] = x->peer[p];
     sink.done = x->d_done;
     sink.track_map = d_track_map; sink.n_map = (uint32_t)n_map;
-    int rc = aid_match_device_out(e, d_hash, d_t, d_hash_off, d_hash_len, d_status, n_q, nullptr, max_rows, nullptr, sink, st);
+    int rc = aid_match_device_out(e, d_hash, d_t, d_hash_off, d_hash_len, d_status, n_q, nullptr, max_rows, nullptr, sink, st,
+                                  x->d_done + 1);
     if (rc) return rc;
     const long long timeout_cycles = (long long)x->timeout_ms * x->clock_khz;
     { StageTimer tm(e, st, 7);
@@ -327,6 +332,13 @@ extern "C" int aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const f
         max_rows > AID_MAX_ROWS || n_map < 0 || n_map >= ((int64_t)1 << 32)) return AID_E_ARG;
     if (n_windows > 0 && (!d_rows || !d_n_rows)) return AID_E_ARG;
     if (n_windows == 0) return AID_OK;
+    // A vote window is at most AID_QUERY_MAX_FRAMES frames (k_match packs t_query into 15 bits of the vote key and 16 bits
+    // of q_first / q_last). Checked for ALL windows and before the epoch moves: every rank passes the same batch, so every
+    // rank returns the same status and the ranks' epochs stay in step.
+    for (int i = 0; i < n_windows; i++) {
+        if (sample_off[i + 1] < sample_off[i]) return AID_E_ARG;
+        if (aid_num_frames(sample_off[i + 1] - sample_off[i]) > AID_QUERY_MAX_FRAMES) return AID_E_TOO_LONG;
+    }
     AID_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->slot[0].st;
     const int P = x->world, r = x->rank;
@@ -350,4 +362,42 @@ extern "C" int aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const f
     return match_and_merge(e, x, epoch, wh, x->lay.t(x->window, parity), x->lay.begins(x->window, parity),
                            x->lay.lens(x->window, parity), nullptr, n_windows, d_track_map, n_map, d_rows, max_rows,
                            d_n_rows, st);
+}
+
+// Host buffers in, host buffers out: what a service process hands over (the windows' PCM in pinned or pageable host
+// memory) and what it gets back (rows of its own slice of the batch, or of all windows). Rank r only needs the PCM of
+// windows [r*n/P, (r+1)*n/P) on its device, so that is all that crosses PCIe; the merged rows of every window end up on
+// every rank and `rows_first / rows_count` says which of them this caller wants copied back.
+extern "C" int aid_identify_exchange_host(aid_engine* e, aid_exchange* x, const float* pcm, const int64_t* sample_off,
+                                          int n_windows, const uint32_t* d_track_map, int64_t n_map,
+                                          int rows_first, int rows_count, aid_match_row* rows, int max_rows,
+                                          int32_t* n_rows) {
+    if (!e || !x || x->e != e || !sample_off || n_windows < 0 || rows_first < 0 || rows_count < 0 ||
+        rows_first + (int64_t)rows_count > n_windows || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
+    if (rows_count > 0 && (!rows || !n_rows)) return AID_E_ARG;
+    if (n_windows == 0) return AID_OK;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Slot& s = e->slot[0];
+    Index* ix = e->index;
+    const int P = x->world, r = x->rank;
+    const int lo = (int)((int64_t)r * n_windows / P), hi = (int)((int64_t)(r + 1) * n_windows / P);
+    const int64_t s0 = sample_off[lo], samples = sample_off[hi] - s0;
+    if (samples < 0 || (samples > 0 && !pcm)) return AID_E_ARG;
+    AID_CUDA(e, s.pcm.ensure((size_t)std::max<int64_t>(samples, 1) * sizeof(float)));
+    AID_CUDA(e, ix->rows.ensure((size_t)n_windows * max_rows * sizeof(aid_match_row)));
+    AID_CUDA(e, ix->rows_n.ensure((size_t)n_windows * 4));
+    if (samples > 0)
+        AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + s0, (size_t)samples * sizeof(float), cudaMemcpyHostToDevice, s.st));
+    // the device entry point indexes d_pcm with the batch's sample offsets: shift the base so that sample s0 is s.pcm[0]
+    int rc = aid_identify_exchange_dev(e, x, s.pcm.as<float>() - s0, sample_off, n_windows, d_track_map, n_map,
+                                       ix->rows.as<aid_match_row>(), max_rows, ix->rows_n.as<int32_t>(), s.st);
+    if (rc) return rc;
+    if (rows_count > 0) {
+        AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.as<aid_match_row>() + (int64_t)rows_first * max_rows,
+                                    (size_t)rows_count * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, s.st));
+        AID_CUDA(e, cudaMemcpyAsync(n_rows, ix->rows_n.as<int32_t>() + rows_first, (size_t)rows_count * 4, cudaMemcpyDeviceToHost, s.st));
+    }
+    AID_CUDA(e, cudaStreamSynchronize(s.st));
+    for (int i = 0; i < rows_count; i++) if (n_rows[i] < 0) return AID_E_TIMEOUT;
+    return AID_OK;
 }

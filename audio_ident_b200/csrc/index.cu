@@ -18,7 +18,9 @@
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
 #include "engine.h"
 #include "index.h"
@@ -158,7 +160,7 @@ void aid_index_free(aid_engine*, Index* ix) {
     for (Segment* s : ix->segs) { s->release(); delete s; }
     for (SegGroup* g : ix->groups) { if (g) { g->release(); delete g; } }
     ix->cursor.release(); ix->scan_tmp.release(); ix->d_jobs.release(); ix->d_segdesc.release(); ix->group_start.release();
-    ix->cand.release(); ix->cand_n.release(); ix->rows.release(); ix->rows_n.release();
+    ix->cand.release(); ix->cand_n.release(); ix->rows.release(); ix->rows_n.release(); ix->vote_stats.release();
     delete ix;
 }
 
@@ -371,12 +373,16 @@ int aid_index_commit_on(aid_engine* e, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------- C ABI
+// fp_*: optional host copies of the fingerprints that were stored (aid_index_add_host_fp; the caller journals them)
 static int add_pcm(aid_engine* e, const float* pcm, bool on_device, const int64_t* sample_off, int n_tracks,
-                   const char* const* names, uint8_t* ok) {
+                   const char* const* names, uint8_t* ok, uint32_t* fp_hash = nullptr, uint32_t* fp_t = nullptr,
+                   int64_t fp_cap = 0, int64_t* fp_off = nullptr) {
     if (!e || !sample_off || !names || !ok || n_tracks < 0) return AID_E_ARG;
     if (n_tracks > 0 && !pcm && sample_off[n_tracks] > sample_off[0]) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
     Slot& s = e->slot[0];
+    int64_t fp_pos = 0;
+    if (fp_off) fp_off[0] = 0;
     for (int first = 0; first < n_tracks;) {
         int64_t frames = 0; int count = 0;
         while (first + count < n_tracks) {
@@ -406,9 +412,27 @@ static int add_pcm(aid_engine* e, const float* pcm, bool on_device, const int64_
         for (int i = 0; i < count; i++) nf[i] = aid_num_frames(sample_off[first + i + 1] - sample_off[first + i]);
         if ((rc = aid_index_append(e, s.hash.as<uint32_t>(), s.t.as<uint32_t>(), h_off.data(), h_st.data(), nf.data(),
                                    count, names + first, ok + first, s.st))) return rc;
+        if (fp_off) {                                  // the sub-batch's dense fingerprints, device order, one copy each
+            const int64_t total = h_off[count];
+            if (fp_pos + total > fp_cap) return AID_E_CAPACITY;
+            if (total > 0) {
+                AID_CUDA(e, cudaMemcpyAsync(fp_hash + fp_pos, s.hash.p, (size_t)total * 4, cudaMemcpyDeviceToHost, s.st));
+                AID_CUDA(e, cudaMemcpyAsync(fp_t + fp_pos, s.t.p, (size_t)total * 4, cudaMemcpyDeviceToHost, s.st));
+                AID_CUDA(e, cudaStreamSynchronize(s.st));
+            }
+            for (int i = 0; i < count; i++) fp_off[first + i + 1] = fp_pos + h_off[i + 1];
+            fp_pos += total;
+        }
         first += count;
     }
     return AID_OK;
+}
+
+extern "C" int aid_index_add_host_fp(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
+                                     const char* const* names, uint8_t* ok, uint32_t* hash, uint32_t* t_anchor,
+                                     int64_t hash_cap, int64_t* hash_off) {
+    if (!hash_off || hash_cap < 0 || (hash_cap > 0 && (!hash || !t_anchor))) return AID_E_ARG;
+    return add_pcm(e, pcm, false, sample_off, n_tracks, names, ok, hash, t_anchor, hash_cap, hash_off);
 }
 
 extern "C" int aid_index_add_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
@@ -424,6 +448,17 @@ extern "C" int aid_index_add_hashes(aid_engine* e, const uint32_t* hash, const u
                                     const int64_t* hash_off, const int64_t* n_frames, int n_tracks,
                                     const char* const* names, uint8_t* ok) {
     if (!e || !hash_off || !n_frames || !names || !ok || n_tracks < 0) return AID_E_ARG;
+    // This entry point is fed from disk (journal replay) and from other ranks: nothing unchecked reaches the device.
+    // A hash outside AID_HASH_BITS would index past the bucket table / directory in k_hist, a t_anchor outside the
+    // track would spill into the local-track bits of the posting.
+    for (int i = 0; i < n_tracks; i++) {
+        if (hash_off[i + 1] < hash_off[i]) return AID_E_ARG;
+        if (hash_off[i + 1] > hash_off[i] && (!hash || !t_anchor)) return AID_E_ARG;
+        if (n_frames[i] > AID_INDEX_MAX_FRAMES) continue;      // refused by aid_index_append (ok[i] = 0), never copied
+        const int64_t t_lim = std::max<int64_t>(n_frames[i], 0);
+        for (int64_t j = hash_off[i]; j < hash_off[i + 1]; j++)
+            if ((hash[j] >> AID_HASH_BITS) != 0 || (int64_t)t_anchor[j] >= t_lim) return AID_E_ARG;
+    }
     AID_CUDA(e, cudaSetDevice(e->device));
     Slot& s = e->slot[0];
     const int chunk = 4096;
@@ -558,8 +593,12 @@ extern "C" int aid_index_save(aid_engine* e, const char* dir) {
             good = good && wr(f, buf.data(), (size_t)n * 4);
         }
     }
+    // durable before it replaces the old snapshot (the caller drops its journal right after): data, then the rename
+    good = good && fflush(f) == 0 && fsync(fileno(f)) == 0;
     good = (fclose(f) == 0) && good;
     if (!good || rename(tmp.c_str(), fin.c_str()) != 0) { e->err = std::string("cannot write ") + fin + ": " + strerror(errno); remove(tmp.c_str()); return AID_E_IO; }
+    const int dfd = open(dir, O_RDONLY | O_DIRECTORY);
+    if (dfd >= 0) { fsync(dfd); close(dfd); }
     return AID_OK;
 }
 
@@ -605,6 +644,11 @@ extern "C" int aid_index_load(aid_engine* e, const char* dir) {
         buf.resize((size_t)n);
         for (DevBuf* dst : {&s->st_hash, &s->st_post}) {
             good = good && rd(f, buf.data(), (size_t)n * 4);
+            // a damaged file must not reach the device: hashes index the 2^24-entry tables, postings name local tracks
+            if (good) {
+                const uint64_t lim = dst == &s->st_hash ? ((uint64_t)1 << AID_HASH_BITS) : ((uint64_t)nt << AID_POST_T_BITS);
+                for (uint64_t i = 0; i < n && good; i++) good = (uint64_t)buf[(size_t)i] < lim;
+            }
             if (ce == cudaSuccess) ce = dst->ensure(std::max<size_t>((size_t)n, 1) * 4);
             if (ce == cudaSuccess && n && good) ce = cudaMemcpy(dst->p, buf.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
         }

@@ -60,6 +60,7 @@ struct Index {
     bool segdesc_dirty = true;
     // matcher workspace
     DevBuf cand, cand_n, rows, rows_n;
+    DevBuf vote_stats;                                   // u64[1024][2]: hashes probed, postings touched (aid_match_stats)
 };
 
 // ---- sharded identification over peer memory (exchange.cu) ---------------------------------------------------
@@ -119,7 +120,8 @@ struct RowSink {
 // match.cu: probe + vote + rank for n_q windows; rows go to (d_rows, d_n_rows) or, with sink.world > 0, to the peers
 int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
                          const uint32_t* d_hash_len, const int32_t* d_status, int n_q, aid_match_row* d_rows,
-                         int max_rows, int32_t* d_n_rows, const RowSink& sink, cudaStream_t st);
+                         int max_rows, int32_t* d_n_rows, const RowSink& sink, cudaStream_t st,
+                         const uint32_t* d_abort /* device flag: non-zero = probe nothing (may be null) */);
 
 int aid_index_commit_on(aid_engine* e, cudaStream_t st);
 int aid_index_append(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* h_off,

@@ -101,10 +101,17 @@ __global__ void __launch_bounds__(kThreads)
 k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, const uint32_t* __restrict__ hash_off,
         const uint32_t* __restrict__ hash_len, const int32_t* __restrict__ q_status,
         const aid_seg_desc* __restrict__ segs, int n_seg,
-        CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n) {
+        CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n,
+        const uint32_t* __restrict__ abort_flag, unsigned long long* __restrict__ vote_stats) {
     __shared__ MatchSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = blockIdx.x / n_seg, sg = blockIdx.x % n_seg;
+    // sharded identification: the wait for the peers' query fingerprints gave up (k_wait_hashes) -- the hash window is
+    // only partly written, so nothing is probed; k_rank still publishes (empty) blocks and the merge reports -1 rows
+    if (abort_flag && *abort_flag) {
+        if (tid == 0) cand_n[blockIdx.x] = 0;
+        return;
+    }
     const aid_seg_desc seg = segs[sg];
     const uint32_t h0 = hash_off[q];
     const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : (hash_len ? hash_len[q] : hash_off[q + 1] - h0);
@@ -188,6 +195,11 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
         }
         __syncthreads();
         total = sm.total;
+    }
+    // bench.py's roofline numerator: hashes probed and postings touched, spread over 1024 counters
+    if (vote_stats && tid == 0) {
+        atomicAdd(vote_stats + 2 * (blockIdx.x & 1023u), (unsigned long long)nh);
+        atomicAdd(vote_stats + 2 * (blockIdx.x & 1023u) + 1, (unsigned long long)total);
     }
     if (total < AID_MIN_VOTES) {
         if (tid == 0) cand_n[blockIdx.x] = 0;
@@ -395,7 +407,7 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
 // Rows and counts are written to device memory (d_rows[n_q][max_rows], d_n_rows[n_q]); asynchronous on st.
 int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t, const uint32_t* d_hash_off,
                          const uint32_t* d_hash_len, const int32_t* d_status, int n_q, aid_match_row* d_rows,
-                         int max_rows, int32_t* d_n_rows, const RowSink& sink, cudaStream_t st) {
+                         int max_rows, int32_t* d_n_rows, const RowSink& sink, cudaStream_t st, const uint32_t* d_abort) {
     Index* ix = e->index;
     int rc = aid_index_commit_on(e, st);
     if (rc) return rc;
@@ -413,9 +425,17 @@ int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* 
     if (n_cta >= ((int64_t)1 << 31)) return AID_E_ARG;
     AID_CUDA(e, ix->cand.ensure((size_t)n_cta * AID_MAX_ROWS * sizeof(CandEntry)));
     AID_CUDA(e, ix->cand_n.ensure((size_t)n_cta * 4));
+    unsigned long long* stats = nullptr;
+    if (e->timing) {                                  // probe statistics ride along with the stage timing (bench.py)
+        if (!ix->vote_stats.p) {
+            AID_CUDA(e, ix->vote_stats.ensure(2 * 1024 * sizeof(unsigned long long)));
+            AID_CUDA(e, cudaMemsetAsync(ix->vote_stats.p, 0, 2 * 1024 * sizeof(unsigned long long), st));
+        }
+        stats = ix->vote_stats.as<unsigned long long>();
+    }
     { StageTimer tm(e, st, 4);
     k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
-                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>()); }
+                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), d_abort, stats); }
     { StageTimer tm(e, st, 5);
     k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
                                      max_rows, d_rows, d_n_rows, sink); }
@@ -433,7 +453,7 @@ static int match_device(aid_engine* e, const uint32_t* d_hash, const uint32_t* d
     AID_CUDA(e, ix->rows.ensure((size_t)n_q * max_rows * sizeof(aid_match_row)));
     AID_CUDA(e, ix->rows_n.ensure((size_t)n_q * 4));
     int rc = aid_match_device_out(e, d_hash, d_t, d_hash_off, nullptr, d_status, n_q, ix->rows.as<aid_match_row>(), max_rows,
-                                  ix->rows_n.as<int32_t>(), RowSink{}, st);
+                                  ix->rows_n.as<int32_t>(), RowSink{}, st, nullptr);
     if (rc) return rc;
     AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.p, (size_t)n_q * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, st));
     AID_CUDA(e, cudaMemcpyAsync(n_rows, ix->rows_n.p, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
@@ -448,7 +468,21 @@ extern "C" int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32
     if (n_queries > 0 && (!d_hash_off || !d_rows || !d_n_rows)) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
     return aid_match_device_out(e, d_hash, d_t_anchor, d_hash_off, d_hash_len, d_status, n_queries, d_rows, max_rows, d_n_rows,
-                                RowSink{}, stream ? (cudaStream_t)stream : e->slot[0].st);
+                                RowSink{}, stream ? (cudaStream_t)stream : e->slot[0].st, nullptr);
+}
+
+extern "C" int aid_match_stats(aid_engine* e, int64_t* out) {
+    if (!e || !out) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    Index* ix = e->index;
+    out[0] = out[1] = 0;
+    if (!ix->vote_stats.p) return AID_OK;
+    AID_CUDA(e, cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(2 * 1024);
+    AID_CUDA(e, cudaMemcpy(h.data(), ix->vote_stats.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 1024; i++) { out[0] += (int64_t)h[2 * i]; out[1] += (int64_t)h[2 * i + 1]; }
+    AID_CUDA(e, cudaMemset(ix->vote_stats.p, 0, h.size() * sizeof(unsigned long long)));
+    return AID_OK;
 }
 
 extern "C" int aid_copy_device(aid_engine* e, void* d_dst, const void* d_src, int64_t bytes, void* stream) {

@@ -215,6 +215,26 @@ class Engine:
         self._check(fn(self._h, _ptr(pcm), offp, n, self._names(names), ok.ctypes.data_as(C.POINTER(C.c_uint8))))
         return ok[:n].astype(bool)
 
+    def index_add_fp(self, pcm, sample_off, names: Sequence[str]):
+        """index_add on host PCM that also returns the stored fingerprints (for the caller's journal):
+        (ok bool[n], hash u32, t_anchor u32, hash_off i64[n+1])."""
+        sample_off, offp = self._off(sample_off)
+        n = len(sample_off) - 1
+        if len(names) != n:
+            raise ValueError("one name per track")
+        if isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+        cap = self.hash_capacity(sample_off)
+        h = np.empty(max(cap, 1), np.uint32)
+        t = np.empty(max(cap, 1), np.uint32)
+        hoff = np.zeros(n + 1, np.int64)
+        ok = np.zeros(max(n, 1), np.uint8)
+        self._check(self._L.aid_index_add_host_fp(self._h, _ptr(pcm), offp, n, self._names(names),
+                                                  ok.ctypes.data_as(C.POINTER(C.c_uint8)), h.ctypes.data, t.ctypes.data, cap,
+                                                  hoff.ctypes.data_as(C.POINTER(C.c_int64))))
+        total = int(hoff[n])
+        return ok[:n].astype(bool), h[:total], t[:total], hoff
+
     def index_add_hashes(self, h, t, hash_off, n_frames, names: Sequence[str]) -> np.ndarray:
         hash_off, offp = self._off(hash_off)
         n_frames, nfp = self._off(n_frames)
@@ -315,6 +335,23 @@ class Engine:
         self._check(self._L.aid_identify_exchange_dev(self._h, xchg._h, _ptr(d_pcm), offp, len(sample_off) - 1,
                                                       _ptr(d_track_map), int(n_map), _ptr(d_rows), int(max_rows),
                                                       _ptr(d_n_rows), _ptr(stream)))
+
+    def identify_exchange_host(self, xchg: "Exchange", pcm, sample_off, d_track_map, n_map: int, rows: np.ndarray,
+                               n_rows: np.ndarray, rows_first: int = 0, rows_count: int | None = None,
+                               max_rows: int = MAX_ROWS) -> None:
+        """aid_identify_exchange_host: host window PCM in (only this rank's slice crosses PCIe), merged rows of windows
+        [rows_first, rows_first + rows_count) back in the caller's host arrays (MATCH_ROW_DTYPE [count, max_rows])."""
+        sample_off, offp = self._off(sample_off)
+        n = len(sample_off) - 1
+        cnt = n - rows_first if rows_count is None else int(rows_count)
+        self._check(self._L.aid_identify_exchange_host(self._h, xchg._h, _ptr(pcm), offp, n, _ptr(d_track_map), int(n_map),
+                                                       int(rows_first), cnt, _ptr(rows), int(max_rows), _ptr(n_rows)))
+
+    def match_stats(self) -> tuple[int, int]:
+        """(query hashes looked up, postings touched) by k_match since the last call, while stage timing was on."""
+        out = np.zeros(2, np.int64)
+        self._check(self._L.aid_match_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return int(out[0]), int(out[1])
 
     def copy_device(self, d_dst, d_src, nbytes: int, stream=None) -> None:
         self._check(self._L.aid_copy_device(self._h, _ptr(d_dst), _ptr(d_src), int(nbytes), _ptr(stream)))

@@ -21,6 +21,13 @@ worker thread so the event loop is never blocked -- ctypes releases the GIL) ins
 (``journal.bin``); an emptied directory is an empty index (``make rebuild-index``, Makefile:84-93).
 
 Additive batch API: ``index_tracks`` and ``query_many``.
+
+Micro-batching: the unmodified exact lane awaits ``olaf_query`` once per sub-window
+(exact.py:150-171) and many requests run concurrently on the event loop, so ``olaf_query`` does not call the engine
+itself: it hands its window to a process-wide batcher thread that collects whatever arrives within
+``AID_BATCH_WAIT_MS`` (default 2 ms; or until ``AID_BATCH_MAX_WINDOWS``, default 4096) and issues ONE engine call
+for all of them -- concurrent coroutines share a GPU pass instead of queueing batch-of-1 launches behind a lock.
+
 There is no CPU fallback: if the CUDA engine cannot be opened every entry point raises ``OlafError``.
 """
 from __future__ import annotations
@@ -30,6 +37,7 @@ import logging
 import os
 import struct
 import threading
+import time
 import uuid
 from dataclasses import dataclass
 from pathlib import Path
@@ -90,29 +98,69 @@ def _journal_path(d: Path) -> Path:
 
 
 def _replay_journal(eng, path: Path) -> int:
+    """Re-applies the journal in order. Consecutive additions go to the engine as one batch (one ctypes call, one
+    dirty-segment mark); a deletion or a repeated name flushes the batch so the order of effects is kept. The engine
+    validates every record (hash / t_anchor ranges: a damaged file must not reach the device); replay stops at the
+    first record that fails or does not parse -- what follows a damaged record cannot be trusted."""
     if not path.exists():
         return 0
     data = path.read_bytes()
     pos, n = 0, 0
+    batch: list[tuple[str, int, np.ndarray, np.ndarray]] = []
+    names_in_batch: set[str] = set()
+
+    def flush() -> bool:
+        if not batch:
+            return True
+        hs = np.concatenate([b[2] for b in batch]) if batch else np.zeros(0, np.uint32)
+        ts = np.concatenate([b[3] for b in batch]) if batch else np.zeros(0, np.uint32)
+        off = np.concatenate([[0], np.cumsum([len(b[2]) for b in batch])])
+        try:
+            eng.index_add_hashes(hs, ts, off, [b[1] for b in batch], [b[0] for b in batch])
+            good = True
+        except Exception as exc:                                    # find the first bad record of this batch
+            good = False
+            for name, n_frames, h, t in batch:
+                try:
+                    eng.index_add_hashes(h, t, [0, len(h)], [n_frames], [name])
+                except Exception:
+                    logger.error("journal %s: record for track %s is damaged (%s); replay stops there", path, name, exc)
+                    break
+        batch.clear(); names_in_batch.clear()
+        return good
+
     while pos + 24 <= len(data):
         magic, kind, name_len, n_frames, n_hash = struct.unpack_from("<4sIIqI", data, pos)
-        if magic != _JOURNAL_MAGIC:
+        if magic != _JOURNAL_MAGIC or kind not in (_JOURNAL_ADD, _JOURNAL_DEL) or name_len > 4096:
+            logger.error("journal %s: unreadable record at byte %d; replay stops there", path, pos)
             break
         end = pos + 24 + name_len + (8 * n_hash if kind == _JOURNAL_ADD else 0)
         if end > len(data):
             break                                     # torn tail: the last call did not complete
-        name = data[pos + 24:pos + 24 + name_len].decode()
+        try:
+            name = data[pos + 24:pos + 24 + name_len].decode()
+        except UnicodeDecodeError:
+            logger.error("journal %s: unreadable track name at byte %d; replay stops there", path, pos)
+            break
         if kind == _JOURNAL_ADD:
             arr = np.frombuffer(data, dtype="<u4", count=2 * n_hash, offset=pos + 24 + name_len)
-            eng.index_add_hashes(arr[:n_hash], arr[n_hash:], [0, n_hash], [n_frames], [name])
-        elif kind == _JOURNAL_DEL:
+            if name in names_in_batch or len(batch) >= 4096:
+                if not flush():
+                    return n
+            batch.append((name, int(n_frames), arr[:n_hash], arr[n_hash:]))
+            names_in_batch.add(name)
+        else:
+            if not flush():
+                return n
             eng.index_delete(name)
         pos = end
         n += 1
+    flush()
     return n
 
 
-def _append_journal(kind: int, name: str, n_frames: int = 0, h: np.ndarray | None = None, t: np.ndarray | None = None) -> None:
+def _append_journal(kind: int, name: str, n_frames: int = 0, h: np.ndarray | None = None, t: np.ndarray | None = None,
+                    sync: bool = True) -> None:
     d = _state.dir
     if d is None:
         return
@@ -125,6 +173,9 @@ def _append_journal(kind: int, name: str, n_frames: int = 0, h: np.ndarray | Non
             f.write(np.ascontiguousarray(h, "<u4").tobytes())
             f.write(np.ascontiguousarray(t, "<u4").tobytes())
         _state.journal_bytes = f.tell()
+        if sync:
+            f.flush()
+            os.fsync(f.fileno())                        # the caller is about to report the track as indexed
     if _state.journal_bytes > _CHECKPOINT_BYTES:
         checkpoint()
 
@@ -165,10 +216,15 @@ def checkpoint() -> None:
     with _state.lock:
         if _state.engine is None or _state.dir is None:
             return
-        _state.engine.index_save(str(_state.dir))
+        _state.engine.index_save(str(_state.dir))      # data and rename are fsynced before this returns (aid_index_save)
         jp = _journal_path(_state.dir)
         if jp.exists():
             jp.unlink()
+            try:
+                fd = os.open(str(_state.dir), os.O_RDONLY)
+                os.fsync(fd); os.close(fd)
+            except OSError:
+                pass
         _state.journal_bytes = 0
 
 
@@ -197,24 +253,18 @@ def index_tracks_sync(items: Sequence[tuple[bytes, uuid.UUID]]) -> list[bool]:
     eng = get_engine()
     with _state.lock:
         pcm, off = ragged([items[i][0] for i in live])
-        h, t, hoff, st = eng.fingerprint(pcm, off)
         names = [str(items[i][1]) for i in live]
         frames = [_frames(int(off[k + 1] - off[k])) for k in range(len(live))]
-        good = [k for k in range(len(live)) if not (st[k] & 3)]
-        if good:
-            sel_h = np.concatenate([h[hoff[k]:hoff[k + 1]] for k in good]) if good else h[:0]
-            sel_t = np.concatenate([t[hoff[k]:hoff[k + 1]] for k in good]) if good else t[:0]
-            sel_off = np.concatenate([[0], np.cumsum([hoff[k + 1] - hoff[k] for k in good])])
-            ok = eng.index_add_hashes(sel_h, sel_t, sel_off, [frames[k] for k in good], [names[k] for k in good])
-            for j, k in enumerate(good):
-                if ok[j]:
-                    _append_journal(_JOURNAL_ADD, names[k], frames[k], h[hoff[k]:hoff[k + 1]], t[hoff[k]:hoff[k + 1]])
-                    out[live[k]] = True
-                else:
-                    logger.error("engine refused track %s (longer than the index limit?)", names[k])
+        # one engine call: fingerprint, store from the device buffers, and the stored fingerprints back for the journal
+        ok, h, t, hoff = eng.index_add_fp(pcm, off, names)
+        last = max((k for k in range(len(live)) if ok[k]), default=-1)
         for k in range(len(live)):
-            if st[k] & 3:
-                logger.error("fingerprinting failed for track %s (status %d)", names[k], int(st[k]))
+            if ok[k]:
+                _append_journal(_JOURNAL_ADD, names[k], frames[k], h[hoff[k]:hoff[k + 1]], t[hoff[k]:hoff[k + 1]],
+                                sync=(k == last))
+                out[live[k]] = True
+            else:
+                logger.error("engine refused track %s (fingerprinting failed or longer than the index limit)", names[k])
     return out
 
 
@@ -260,6 +310,74 @@ async def _in_thread(fn, *args):
     return await asyncio.get_running_loop().run_in_executor(None, fn, *args)
 
 
+class _QueryBatcher:
+    """Collects the windows of concurrent olaf_query coroutines into one engine call.
+
+    A single daemon thread owns the query side of the engine: it sleeps until a window arrives, keeps collecting for at
+    most `wait_s` (or until `max_windows`), then runs query_many_sync on the lot and hands every coroutine its own
+    list through its event loop. While a GPU pass is in flight the next batch fills up by itself, so under load the
+    wait never adds latency; an idle service pays at most `wait_s` (2 ms of a 3 s budget, orchestrator.py:31)."""
+
+    def __init__(self) -> None:
+        self.wait_s = float(os.environ.get("AID_BATCH_WAIT_MS", "2")) / 1e3
+        self.max_windows = int(os.environ.get("AID_BATCH_MAX_WINDOWS", "4096"))
+        self._cv = threading.Condition()
+        self._pending: list[tuple[bytes, asyncio.AbstractEventLoop, asyncio.Future]] = []
+        self._thread: threading.Thread | None = None
+        self.engine_calls = 0                     # statistics (tests, /metrics)
+        self.windows = 0
+
+    def submit(self, pcm: bytes) -> "asyncio.Future":
+        loop = asyncio.get_running_loop()
+        fut = loop.create_future()
+        with self._cv:
+            if self._thread is None or not self._thread.is_alive():
+                self._thread = threading.Thread(target=self._run, name="aid-query-batcher", daemon=True)
+                self._thread.start()
+            self._pending.append((pcm, loop, fut))
+            self._cv.notify()
+        return fut
+
+    @staticmethod
+    def _deliver(loop, fut, result, exc) -> None:
+        def done():
+            if fut.cancelled():
+                return
+            if exc is not None:
+                fut.set_exception(exc)
+            else:
+                fut.set_result(result)
+        try:
+            loop.call_soon_threadsafe(done)
+        except RuntimeError:                      # the caller's loop is gone (request cancelled, loop closed)
+            pass
+
+    def _run(self) -> None:
+        while True:
+            with self._cv:
+                while not self._pending:
+                    self._cv.wait()
+                deadline = time.monotonic() + self.wait_s
+                while len(self._pending) < self.max_windows:
+                    left = deadline - time.monotonic()
+                    if left <= 0:
+                        break
+                    self._cv.wait(left)
+                batch, self._pending = self._pending[:self.max_windows], self._pending[self.max_windows:]
+            try:
+                results = query_many_sync([b[0] for b in batch])
+                self.engine_calls += 1
+                self.windows += len(batch)
+                for (_, loop, fut), res in zip(batch, results):
+                    self._deliver(loop, fut, res, None)
+            except BaseException as exc:          # noqa: BLE001 -- every waiter must hear about it
+                for _, loop, fut in batch:
+                    self._deliver(loop, fut, None, exc)
+
+
+_batcher = _QueryBatcher()
+
+
 # --------------------------------------------------------------------------------------- public API
 async def olaf_index_track(pcm_16k_f32le: bytes, track_id: uuid.UUID) -> bool:
     """Index a track's fingerprint hashes. ``b""`` -> False without touching the engine; an engine-side
@@ -282,7 +400,7 @@ async def olaf_query(pcm_16k_f32le: bytes) -> list[OlafMatch]:
     if not pcm_16k_f32le:
         return []
     try:
-        return (await _in_thread(query_many_sync, [pcm_16k_f32le]))[0]
+        return await _batcher.submit(pcm_16k_f32le)
     except OlafError:
         raise
     except Exception as exc:

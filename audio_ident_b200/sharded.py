@@ -2,13 +2,20 @@
 
 Sharding (DESIGN.md "Multi-GPU"): tracks are dealt to ranks round-robin (global track g lives on rank g % P) and
 each rank holds ordinary index segments for its own tracks. A (track, offset) vote histogram therefore lives
-entirely on one rank, every rank can apply the AID_MIN_VOTES threshold and keep its exact top-50 locally, and the
-only exchange is one all-gather of the fixed-size per-rank row blocks (50 rows x 20 B per query) over
-NCCL/NVLink, after which every rank performs the same merge: order by (count desc, global track asc, offset asc),
-keep 50. The result is bit-identical to a single index holding all tracks (tests/test_sharded_cpu.py,
-tests/test_gpu_sharded.py). Hash-range sharding, which BASELINE.json's north_star sketches, would split every
-histogram across ranks, so no rank could threshold and all partial (track, offset, count) tuples -- not 50 rows --
-would have to cross NVLink; see DESIGN.md for the byte counts behind that decision.
+entirely on one rank, every rank can apply the AID_MIN_VOTES threshold and keep its exact top-50 locally, and what
+has to meet is the per-rank rows; every rank then performs the same merge: order by (count desc, global track asc,
+offset asc), keep 50. The result is bit-identical to a single index holding all tracks (tests/test_sharded_cpu.py,
+tests/test_gpu_sharded.py, tests/test_gpu_ipc_exchange.py).
+
+Query paths, in the order `query` prefers them:
+  * fused (product path; `enable_peer_exchange`): one engine call, aid_identify_exchange_dev / _host -- split
+    fingerprinting, fingerprints and rows exchanged through peer memory from inside the kernels, device merge;
+  * NCCL (`_query_device`; comparison, and batches larger than the exchange was sized for): all-gather of padded
+    fingerprints, local probe, all-gather of 50-row blocks, torch sort;
+  * host split (`device=False`, gloo tests on CPU backends): the same exchange through host arrays.
+Hash-range sharding, which BASELINE.json's north_star sketches, would split every histogram across ranks, so no
+rank could threshold and all partial (track, offset, count) tuples -- not 50 rows -- would have to cross NVLink;
+DESIGN.md section 5 has the byte counts and the measurement behind that decision.
 
 Bulk ingest needs no collective at all: each rank fingerprints and stores its own tracks.
 """
@@ -244,14 +251,47 @@ class ShardedIdentifier:
         raw = torch.from_numpy(rows.view(np.int32).reshape(n_q, rows.shape[1], 5)).to(self.device, non_blocking=True)
         return self._merge_device(raw, torch.from_numpy(n).to(self.device, non_blocking=True))
 
-    def query(self, pcm, sample_off, device: bool = False, split_fingerprint: bool = True):
+    def check(self) -> None:
+        """Raises EngineError if a step of the peer exchange gave up waiting for a rank (AID_E_TIMEOUT) or a rank's
+        fingerprints did not fit the window (AID_E_CAPACITY). Synchronises the device; reports a failure once."""
+        if self._xchg is not None:
+            self._xchg.check()
+
+    def query_host(self, pcm, sample_off, rows_first: int = 0, rows_count: int | None = None):
+        """Host window PCM in, host rows out, through the fused exchange (aid_identify_exchange_host): only this
+        rank's slice of the batch crosses PCIe. `pcm` is a host array (or an address such that pcm[sample_off[i]] is the
+        first sample of window i for this rank's slice). Returns (rows MATCH_ROW_DTYPE [count, 50] with GLOBAL track
+        numbers, n_rows int32 [count]) for windows [rows_first, rows_first + rows_count). Raises on a failed exchange."""
+        import torch
+        from ._lib import MATCH_ROW_DTYPE
+        if self._xchg is None:
+            raise RuntimeError("enable_peer_exchange() first")
+        sample_off = np.ascontiguousarray(sample_off, np.int64)
+        n = len(sample_off) - 1
+        cnt = n - rows_first if rows_count is None else int(rows_count)
+        if self._map_dev is None:
+            self._map_dev = torch.tensor(self.to_global if self.to_global else [0], dtype=torch.int32, device=self.device)
+        if getattr(self, "_host_rows", None) is None or self._host_rows.shape[0] < cnt:
+            self._host_rows_t = torch.empty((max(cnt, 1), MAX_ROWS * 5), dtype=torch.int32, pin_memory=True)
+            self._host_n_t = torch.empty(max(cnt, 1), dtype=torch.int32, pin_memory=True)
+            self._host_rows = self._host_rows_t.numpy().view(MATCH_ROW_DTYPE).reshape(-1, MAX_ROWS)
+        self.backend.identify_exchange_host(self._xchg, pcm, sample_off, self._map_dev, len(self.to_global),
+                                            self._host_rows_t, self._host_n_t, rows_first, cnt)
+        return self._host_rows[:cnt], self._host_n_t.numpy()[:cnt]
+
+    def query(self, pcm, sample_off, device: bool = False, split_fingerprint: bool = True, check: bool = True):
         """Every rank passes the same query batch. With several ranks the fingerprinting itself is split (rank r
-        fingerprints windows [r*n/P, (r+1)*n/P), hashes are all-gathered) so that no stage is replicated."""
+        fingerprints windows [r*n/P, (r+1)*n/P)) so that no stage is replicated. With the peer exchange enabled the
+        step is asynchronous; check=True (default) waits for it and raises if a rank failed to deliver -- a failed
+        exchange must not read as "no match". Callers that pipeline steps pass check=False and call check() later."""
         sample_off = np.ascontiguousarray(sample_off, np.int64)
         n = len(sample_off) - 1
         if device and self.device is not None and split_fingerprint and n >= self.world and hasattr(self.backend, "match_dev"):
             if self._xchg is not None and n <= self._xchg.max_queries:
-                return self._query_fused(pcm, sample_off)
+                out = self._query_fused(pcm, sample_off)
+                if check:
+                    self._xchg.check()
+                return out
             return self._query_device(pcm, sample_off)
         if self.world == 1 or not split_fingerprint or n < self.world:
             rows, nr = self.backend.query(pcm, sample_off, device=device)

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """bench_longform.py -- BASELINE.json configs[4]: a 3-hour synthetic recording, (a) fingerprinted in time slices with
 halos spread over the ranks (no collective; identical to a single pass, tests/test_gpu_longform.py) and (b) identified
-as a continuous stream of overlapping vote windows against a track-sharded index.
+as a continuous stream of overlapping vote windows against a track-sharded index (fused peer-memory exchange).
+
+Library for bench.py (`longform_block`, the `longform` object of the driver-run line) and a CLI:
 
   python bench_longform.py [--gpus N] [--hours 3] [--tracks 20000]
 """
@@ -20,6 +22,124 @@ sys.path.insert(0, ROOT)
 SR = 16000
 
 
+def longform_block(eng, rank, world, dev, seed=42, hours=3.0, tracks=20000, window_s=10.0, hop_s=5.0, steps=3, warmup=2):
+    """Builds a `tracks`-track sharded index and a `hours`-long recording (random indexed tracks with 6 s noise gaps,
+    the same on every rank), then times (a) the time-sliced fingerprint and (b) the window-stream identification.
+    Returns the result dict on every rank."""
+    import torch
+    import torch.distributed as dist
+    from audio_ident_b200 import longform, sharded
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.index_clear()
+    sh = sharded.ShardedIdentifier(eng, rank, world, device=dev)
+    samples = 30 * SR
+    mine = np.arange(rank, tracks, world, dtype=np.int64)
+    buf = torch.empty(512 * samples, dtype=torch.float32, device=dev)
+    off_full = np.arange(513, dtype=np.int64) * samples
+    for c0 in range(0, len(mine), 512):
+        ids = mine[c0:c0 + 512]
+        if world == 1:
+            eng.synth_tracks(buf.data_ptr(), int(ids[0]), len(ids), samples, seed)
+        else:
+            for j, g in enumerate(ids):
+                eng.synth_tracks(buf.data_ptr() + j * samples * 4, int(g), 1, samples, seed)
+        assert sh.add(buf.data_ptr(), off_full[:len(ids) + 1], [int(g) for g in ids], device=True).all()
+    eng.index_commit()
+    del buf
+
+    # ---- the recording: random indexed tracks with 6 s of low-level noise between them (same on every rank)
+    rng = np.random.default_rng(seed + 5)
+    gap = 6 * SR
+    n_items = int(hours * 3600 * SR) // (samples + gap)
+    playlist = rng.integers(0, tracks, n_items)
+    n_total = n_items * (samples + gap)
+    rec = torch.empty(n_total, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(seed + 9)
+    rec.normal_(0.0, 0.003, generator=gen)
+    one = torch.empty(samples, dtype=torch.float32, device=dev)
+    for k, g in enumerate(playlist):
+        torch.cuda.synchronize()
+        eng.synth_tracks(one.data_ptr(), int(g), 1, samples, seed)
+        eng.sync()
+        rec[k * (samples + gap):k * (samples + gap) + samples] += one
+    rec.clamp_(-1.0, 1.0)
+    torch.cuda.synchronize()
+    rec_hours = n_total / SR / 3600.0
+
+    # ---- (a) time-sliced fingerprint: rank r owns a contiguous range of anchor frames, halo re-read, no collective
+    T = longform.num_frames(n_total)
+    slices = longform.plan_slices(T, world)
+    a, b = slices[min(rank, len(slices) - 1)]
+    s0, s1, e0 = longform.slice_samples(a, b, T)
+    off = np.array([0, s1 - s0], np.int64)
+    stream = torch.cuda.Stream(device=dev)
+    prev = torch.cuda.current_stream(dev)
+    torch.cuda.set_stream(stream)
+
+    def fp_step():
+        return eng.fingerprint_dev(rec.data_ptr() + 4 * s0, off, stream.cuda_stream)
+
+    for _ in range(warmup):
+        fp_step()
+    barrier()
+    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0_.record()
+    for _ in range(steps):
+        res = fp_step()
+    e1_.record()
+    barrier()
+    t_fp = rmax(e0_.elapsed_time(e1_) / steps)
+    n_hash = int(eng.to_host(res.d_hash_off, 2, np.uint32)[1])
+    torch.cuda.set_stream(prev)
+
+    # ---- (b) continuous match stream through the fused exchange
+    n_windows = len(np.unique(longform.plan_windows(n_total, window_s, hop_s)))
+    sh.enable_peer_exchange(n_windows)
+    for _ in range(warmup):
+        segs, m, nn, starts = longform.identify_stream(sh, rec, n_total, window_s, hop_s, device=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        segs, m, nn, starts = longform.identify_stream(sh, rec, n_total, window_s, hop_s, device=True)
+    torch.cuda.synchronize()
+    t_id = rmax((time.perf_counter() - t0) / steps)
+    found = [s.track for s in segs]
+    correct = sum(int(i < len(found) and found[i] == int(g)) for i, g in enumerate(playlist)) if len(found) == len(playlist) else \
+        len(set(found) & set(int(g) for g in playlist))
+    start_err = [abs(-s.offset_frames * 0.008 - k * 36.0) for k, s in enumerate(segs)] if len(found) == len(playlist) else []
+    digest = int(np.bitwise_xor.reduce(((m.astype(np.int64) * np.arange(1, 6)).sum(axis=2).reshape(-1)) & 0xFFFFFFFF))
+    barrier()
+    sh._xchg.close(); sh._xchg = None
+    del rec
+    eng.index_clear()
+    return {
+        "metric": "audio-hours of stream identified/sec", "value": rec_hours / t_id, "unit": "audio-hours/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": t_id * 1e3, "scaling": "strong",
+        "workload": f"{rec_hours:.2f} h recording ({n_items} x 30 s tracks + 6 s gaps), {len(starts)} vote windows of "
+                    f"{window_s:g} s every {hop_s:g} s, index of {tracks} tracks sharded over {world} rank(s)",
+        "timed_region": "recording resident in HBM -> window gather -> fingerprint (windows split over ranks) -> peer-memory "
+                        "exchange -> merged rows -> host segment stitching (wall clock, max over ranks)",
+        "segments_found": len(segs), "playlist_items": int(n_items), "segments_in_order_and_correct": int(correct),
+        "max_start_error_s": max(start_err) if start_err else None, "rows_digest": digest,
+        "sliced_fingerprint": {"ms_per_pass": t_fp, "audio_hours_per_s": rec_hours / (t_fp / 1e3),
+                               "frames_total": int(T), "slices": len(slices), "hashes_rank0": n_hash,
+                               "note": "each rank fingerprints its anchor range plus a 12+33+12-frame halo; no collective; "
+                                       "CUDA events, max over ranks"},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -34,109 +154,23 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from audio_ident_b200 import longform, sharded
     from audio_ident_b200.engine import Engine
 
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/aid_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     eng = Engine(local_rank)
-    sh = sharded.ShardedIdentifier(eng, rank, world, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    samples = 30 * SR
-    mine = np.arange(rank, args.tracks, world, dtype=np.int64)
-    buf = torch.empty(512 * samples, dtype=torch.float32, device=dev)
-    off_full = np.arange(513, dtype=np.int64) * samples
-    for c0 in range(0, len(mine), 512):
-        ids = mine[c0:c0 + 512]
-        for j, g in enumerate(ids):
-            eng.synth_tracks(buf.data_ptr() + j * samples * 4, int(g), 1, samples, args.seed)
-        assert sh.add(buf.data_ptr(), off_full[:len(ids) + 1], [int(g) for g in ids], device=True).all()
-    eng.index_commit()
-    del buf
-
-    # ---- the recording: random indexed tracks with 6 s of low-level noise between them (same on every rank)
-    rng = np.random.default_rng(args.seed + 5)
-    gap = 6 * SR
-    n_items = int(args.hours * 3600 * SR) // (samples + gap)
-    playlist = rng.integers(0, args.tracks, n_items)
-    n_total = n_items * (samples + gap)
-    rec = torch.empty(n_total, dtype=torch.float32, device=dev)
-    gen = torch.Generator(device=dev); gen.manual_seed(args.seed + 9)
-    rec.normal_(0.0, 0.003, generator=gen)
-    one = torch.empty(samples, dtype=torch.float32, device=dev)
-    for k, g in enumerate(playlist):
-        eng.synth_tracks(one.data_ptr(), int(g), 1, samples, args.seed)
-        eng.sync()
-        rec[k * (samples + gap):k * (samples + gap) + samples] += one
-    rec.clamp_(-1.0, 1.0)
-    torch.cuda.synchronize()
-    hours = n_total / SR / 3600.0
-
-    # ---- (a) time-sliced fingerprint: rank r owns a contiguous range of anchor frames, halo re-read, no collective
-    T = longform.num_frames(n_total)
-    slices = longform.plan_slices(T, world)
-    a, b = slices[min(rank, len(slices) - 1)]
-    s0, s1, e0 = longform.slice_samples(a, b, T)
-    off = np.array([0, s1 - s0], np.int64)
-    stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
-
-    def fp_step():
-        return eng.fingerprint_dev(rec.data_ptr() + 4 * s0, off, stream.cuda_stream)
-
-    for _ in range(args.warmup):
-        fp_step()
-    barrier()
-    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0_.record()
-    for _ in range(args.steps):
-        res = fp_step()
-    e1_.record()
-    barrier()
-    t_fp = torch.tensor([e0_.elapsed_time(e1_) / args.steps], dtype=torch.float64, device=dev)
-    n_hash = int(eng.to_host(res.d_hash_off, 2, np.uint32)[1])
-    if world > 1:
-        dist.all_reduce(t_fp, op=dist.ReduceOp.MAX)
-
-    # ---- (b) continuous match stream
-    for _ in range(args.warmup):
-        segs, m, nn, starts = longform.identify_stream(sh, rec, n_total, args.window_s, args.hop_s, device=True)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        segs, m, nn, starts = longform.identify_stream(sh, rec, n_total, args.window_s, args.hop_s, device=True)
-    torch.cuda.synchronize()
-    t_id = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_id, op=dist.ReduceOp.MAX)
-    found = [s.track for s in segs]
-    correct = sum(int(i < len(found) and found[i] == int(g)) for i, g in enumerate(playlist)) if len(found) == len(playlist) else \
-        len(set(found) & set(int(g) for g in playlist))
-    start_err = [abs(-s.offset_frames * 0.008 - k * 36.0) for k, s in enumerate(segs)] if len(found) == len(playlist) else []
+    blk = longform_block(eng, rank, world, dev, args.seed, args.hours, args.tracks, args.window_s, args.hop_s,
+                         args.steps, args.warmup)
     if rank == 0:
-        print(json.dumps({
-            "metric": "audio-hours of stream identified/sec", "value": hours / float(t_id.item()), "unit": "audio-hours/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(t_id.item()) * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32", "data": "synthetic",
-            "config": {"workload": f"{hours:.2f} h recording ({n_items} x 30 s tracks + 6 s gaps), {len(starts)} vote windows of "
-                                   f"{args.window_s:g} s every {args.hop_s:g} s, index of {args.tracks} tracks sharded over {world} rank(s)"},
-            "segments_found": len(segs), "playlist_items": int(n_items), "segments_in_order_and_correct": int(correct),
-            "max_start_error_s": max(start_err) if start_err else None,
-            "sliced_fingerprint": {"ms_per_pass": float(t_fp.item()), "audio_hours_per_s": hours / (float(t_fp.item()) / 1e3),
-                                   "frames_total": int(T), "slices": len(slices), "hashes_rank0": n_hash,
-                                   "note": "each rank fingerprints its anchor range plus a 12+33+12-frame halo; no collective"},
-        }), flush=True)
+        blk.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f32/u32", "data": "synthetic",
+                    "config": {"workload": blk["workload"]}})
+        print(json.dumps(blk), flush=True)
     if world > 1:
         dist.destroy_process_group()
     eng.close()

@@ -125,7 +125,13 @@ int64_t aid_num_frames(int64_t n_samples);
  * fingerprint.py:108). ok[i] = 1 if stored. A name that is already present is replaced. */
 int aid_index_add_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
                        const char* const* names, uint8_t* ok);
-/* Same, PCM already on the device (bulk ingest keeps the PCIe copy out of the way). */
+/* Same, and the fingerprints that were stored come back in host buffers (track i owns hash/t_anchor[hash_off[i] ..
+ * hash_off[i+1]); a track with ok[i] = 0 may own entries, ignore them): the service journals them for persistence
+ * without fingerprinting twice or sending them back up (audio_ident_b200/fingerprint.py). */
+int aid_index_add_host_fp(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_tracks,
+                          const char* const* names, uint8_t* ok, uint32_t* hash, uint32_t* t_anchor,
+                          int64_t hash_cap, int64_t* hash_off /* [n_tracks+1] */);
+/* Same as aid_index_add_host, PCM already on the device (bulk ingest keeps the PCIe copy out of the way). */
 int aid_index_add_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_tracks,
                       const char* const* names, uint8_t* ok);
 /* Adds precomputed fingerprints (hash, t_anchor per track, dense with hash_off) -- used to merge
@@ -170,6 +176,15 @@ int aid_query_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anch
 int aid_match_dev(aid_engine* e, const uint32_t* d_hash, const uint32_t* d_t_anchor, const uint32_t* d_hash_off,
                   const uint32_t* d_hash_len, const int32_t* d_status, int n_queries,
                   aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream);
+/* Precondition of aid_match_dev / aid_match_exchange_dev (the fingerprints are on the device, so it cannot be
+ * checked here): every t_anchor < AID_QUERY_MAX_FRAMES and every hash < 2^AID_HASH_BITS, i.e. the fingerprints
+ * of vote windows of at most AID_QUERY_MAX_FRAMES frames. The entry points that see the PCM or host fingerprints
+ * (aid_query_host/dev, aid_query_hashes, aid_identify_exchange_dev/host) check it and return AID_E_TOO_LONG / AID_E_ARG. */
+
+/* Probe statistics of the matcher kernel since the last call, collected while stage timing is on:
+ * out[0] = query hashes looked up (one directory / table entry each, per segment), out[1] = postings touched.
+ * bench.py's roofline numerator for k_match. Synchronises the device. */
+int aid_match_stats(aid_engine* e, int64_t* out /* [2] */);
 
 /* ---- sharded identification: ranking fused with the row exchange over peer memory ----
  * The reference has one index, so one `olaf_c query` (fingerprint.py:185-193) sees every track. With the index
@@ -200,8 +215,10 @@ int  aid_exchange_connect(aid_exchange* x, const uint8_t* handles);
 int  aid_exchange_connect_local(aid_exchange* x, aid_exchange* const* peers);
 /* how long the merge kernel waits for the slowest rank before it gives up (default 20 s) */
 int  aid_exchange_set_timeout_ms(aid_exchange* x, int64_t ms);
-/* AID_OK; AID_E_TIMEOUT if a kernel gave up waiting for a peer (n_rows of the affected windows are -1);
- * AID_E_CAPACITY if a rank's fingerprints did not fit max_hashes_per_rank (its windows matched nothing). Synchronises. */
+/* AID_OK; AID_E_TIMEOUT if a kernel gave up waiting for a peer (n_rows of the affected windows are -1; after a
+ * failed wait for the peers' fingerprints nothing is probed and every later step reports -1 rows until this call);
+ * AID_E_CAPACITY if a rank's fingerprints did not fit max_hashes_per_rank (its windows matched nothing).
+ * Synchronises; reports a failure once and clears it. */
 int  aid_exchange_status(aid_exchange* x);
 /* aid_match_dev + exchange + merge. d_track_map[n_map] (device, may be NULL) maps this engine's track numbers to
  * global ones; d_rows[n_queries][max_rows] / d_n_rows[n_queries] receive the merged rows. Asynchronous on stream. */
@@ -218,6 +235,16 @@ int  aid_match_exchange_dev(aid_engine* e, aid_exchange* x, const uint32_t* d_ha
 int  aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const float* d_pcm, const int64_t* sample_off,
                                int n_windows, const uint32_t* d_track_map, int64_t n_map, aid_match_row* d_rows,
                                int max_rows, int32_t* d_n_rows, void* stream);
+
+/* The same step from HOST buffers (what a service process holds: the windows' PCM as passed to olaf_query,
+ * fingerprint.py:158-183; pinned memory makes the copies asynchronous): only this rank's slice of the batch crosses
+ * PCIe (rank r fingerprints windows [r*n/world, (r+1)*n/world)), the merged rows of windows
+ * [rows_first, rows_first + rows_count) are copied back into rows[rows_count][max_rows] / n_rows[rows_count].
+ * Synchronous. Returns AID_E_TIMEOUT if a peer did not deliver (n_rows of the affected windows are -1).
+ * With world == 1 this is aid_query_host with the exchange's buffers. */
+int  aid_identify_exchange_host(aid_engine* e, aid_exchange* x, const float* pcm, const int64_t* sample_off,
+                                int n_windows, const uint32_t* d_track_map, int64_t n_map,
+                                int rows_first, int rows_count, aid_match_row* rows, int max_rows, int32_t* n_rows);
 
 /* ---- content-duplicate scan ----------------------------------------------
  * Replaces the per-row Python loop of audio-ident-service/app/audio/dedup.py:170-222 (check_content_duplicate)

@@ -18,7 +18,7 @@ ROW_DTYPE = np.dtype([("count", "<i4"), ("track", "<u4"), ("offset", "<i4"),
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, "aid_oracle.c"), os.path.join(_HERE, "dedup_oracle.c"),
+    srcs = [os.path.join(_HERE, "aid_oracle.c"), os.path.join(_HERE, "dedup_oracle.c"), os.path.join(_HERE, "aid_cpu_f32.c"),
             os.path.join(_HERE, "..", "include", "aid_params.h")]
     stale = (not os.path.exists(_SO)) or force
     if not stale and all(os.path.exists(s) for s in srcs):
@@ -48,6 +48,10 @@ def lib():
         L.aid_oracle_match.argtypes = [u32p, u32p, u64p, u8p, u32p, u32p, C.c_int64, C.c_void_p, C.c_int]
         L.aid_oracle_match.restype = C.c_int
         L.aid_oracle_params.argtypes = [C.POINTER(C.c_int32)]
+        L.aid_cpu_f32_stft.argtypes = [f32p, C.c_int64, f32p]; L.aid_cpu_f32_stft.restype = C.c_int64
+        L.aid_cpu_f32_peaks_from_pcm.argtypes = [f32p, C.c_int64, u32p]; L.aid_cpu_f32_peaks_from_pcm.restype = C.c_int64
+        L.aid_cpu_f32_fingerprint_batch.argtypes = [f32p, i64p, C.c_int, u32p, u32p, i64p, i64p, i64p, C.c_int]
+        L.aid_cpu_f32_fingerprint_batch.restype = C.c_int
         f64p = C.POINTER(C.c_double)
         L.aid_oracle_fp_similarity.argtypes = [u32p, C.c_int64, u32p, C.c_int64]
         L.aid_oracle_fp_similarity.restype = C.c_double
@@ -118,8 +122,29 @@ def fingerprint(pcm: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     return hashes(peaks(stft(pcm)))
 
 
-def fingerprint_batch(pcm: np.ndarray, sample_off: np.ndarray, threads: int = 0):
-    """Ragged batch -> (hash, t_anchor, hash_off[n+1] dense, n_peaks, threads_used)."""
+def stft_f32(pcm: np.ndarray) -> np.ndarray:
+    """The tuned single-precision CPU baseline's spectrogram (aid_cpu_f32.c)."""
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    T = num_frames(len(pcm))
+    S = np.zeros((T, 512), np.float32)
+    if T:
+        lib().aid_cpu_f32_stft(_p(pcm, C.c_float), len(pcm), _p(S, C.c_float))
+    return S
+
+
+def peaks_f32(pcm: np.ndarray) -> np.ndarray:
+    """Peaks of the streaming single-precision baseline, straight from PCM."""
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    keys = np.zeros(max(1, peak_cap(num_frames(len(pcm)))), np.uint32)
+    n = lib().aid_cpu_f32_peaks_from_pcm(_p(pcm, C.c_float), len(pcm), _p(keys, C.c_uint32))
+    if n < 0:
+        raise OverflowError("peak capacity exceeded")
+    return keys[:n].copy()
+
+
+def fingerprint_batch(pcm: np.ndarray, sample_off: np.ndarray, threads: int = 0, f32: bool = False):
+    """Ragged batch -> (hash, t_anchor, hash_off[n+1] dense, n_hash, n_peaks, threads_used).
+    f32=True runs the tuned single-precision streaming baseline (aid_cpu_f32.c) instead of the f64 checker."""
     pcm = np.ascontiguousarray(pcm, np.float32)
     sample_off = np.ascontiguousarray(sample_off, np.int64)
     n = len(sample_off) - 1
@@ -128,7 +153,8 @@ def fingerprint_batch(pcm: np.ndarray, sample_off: np.ndarray, threads: int = 0)
     slot = np.zeros(n + 1, np.int64); slot[1:] = np.cumsum(caps)
     h = np.zeros(max(1, int(slot[-1])), np.uint32); t = np.zeros_like(h)
     nh = np.zeros(n, np.int64); npk = np.zeros(n, np.int64)
-    used = lib().aid_oracle_fingerprint_batch(_p(pcm, C.c_float), _p(sample_off, C.c_int64), n,
+    fn = lib().aid_cpu_f32_fingerprint_batch if f32 else lib().aid_oracle_fingerprint_batch
+    used = fn(_p(pcm, C.c_float), _p(sample_off, C.c_int64), n,
                                               _p(h, C.c_uint32), _p(t, C.c_uint32), _p(slot, C.c_int64),
                                               _p(nh, C.c_int64), _p(npk, C.c_int64), threads)
     off = np.zeros(n + 1, np.int64); off[1:] = np.cumsum(np.maximum(nh, 0))

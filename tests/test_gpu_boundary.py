@@ -93,3 +93,63 @@ def test_queries_do_not_block_the_event_loop(index_dir):
 
     ticks, res = asyncio.run(both())
     assert ticks == 50 and all(r for r in res)
+
+
+def test_concurrent_queries_share_engine_calls(index_dir):
+    """64 olaf_query coroutines in flight at once (what the unmodified exact lane and
+    concurrent requests produce, exact.py:150-171) are served by at most 4 engine calls, and every caller gets exactly
+    the rows a sequential call returns."""
+    tracks = [synth.make_track(700 + k, 12.0) for k in range(8)]
+    ids = [uuid.uuid4() for _ in tracks]
+    assert all(asyncio.run(fp.index_tracks([(x.tobytes(), tid) for x, tid in zip(tracks, ids)])))
+    clips = []
+    for q in range(64):
+        clip, _ = synth.make_query(tracks[q % 8], 300 + q, 5.0, 20.0)
+        clips.append(clip[12000 * (q % 3):12000 * (q % 3) + 56000].tobytes())       # the three sub-window positions
+    sequential = [asyncio.run(fp.olaf_query(c)) for c in clips]
+    assert sum(1 for r in sequential if r) >= 60
+
+    async def burst():
+        return await asyncio.gather(*[fp.olaf_query(c) for c in clips])
+
+    calls0, windows0 = fp._batcher.engine_calls, fp._batcher.windows
+    concurrent = asyncio.run(burst())
+    assert fp._batcher.windows - windows0 == 64
+    assert fp._batcher.engine_calls - calls0 <= 4
+    assert concurrent == sequential
+    # a failing engine call reaches every waiter as OlafError, not a hang
+    real = fp.query_many_sync
+    try:
+        def boom(_clips):
+            raise RuntimeError("injected")
+        fp.query_many_sync = boom
+        with pytest.raises(fp.OlafError):
+            asyncio.run(fp.olaf_query(clips[0]))
+    finally:
+        fp.query_many_sync = real
+    assert asyncio.run(fp.olaf_query(clips[0])) == sequential[0]
+
+
+def test_damaged_journal_is_refused_not_uploaded(index_dir):
+    """journal bytes go through the engine's range checks; replay stops at the damaged record and the
+    records before it survive."""
+    import struct
+    a, b, c = (synth.make_track(800 + k, 8.0) for k in range(3))
+    ia, ib, ic = uuid.uuid4(), uuid.uuid4(), uuid.uuid4()
+    for x, tid in ((a, ia), (b, ib), (c, ic)):
+        assert asyncio.run(fp.olaf_index_track(x.tobytes(), tid))
+    fp.shutdown()
+    jp = index_dir / "journal.bin"
+    data = bytearray(jp.read_bytes())
+    # second record: corrupt its first hash to a value outside the 24-bit hash space
+    pos = 0
+    magic, kind, name_len, n_frames, n_hash = struct.unpack_from("<4sIIqI", data, pos)
+    pos += 24 + name_len + 8 * n_hash
+    magic, kind, name_len, n_frames, n_hash = struct.unpack_from("<4sIIqI", data, pos)
+    assert magic == b"AIDJ" and n_hash > 0
+    struct.pack_into("<I", data, pos + 24 + name_len, 0xFFFFFFFF)
+    jp.write_bytes(bytes(data))
+    rows = asyncio.run(fp.olaf_query(a[16000:16000 * 6].tobytes()))
+    assert rows and rows[0].reference_path == str(ia)                  # the record before the damage is there
+    assert asyncio.run(fp.olaf_query(b[16000:16000 * 6].tobytes())) == []      # the damaged one and what follows are not
+    assert asyncio.run(fp.olaf_query(c[16000:16000 * 6].tobytes())) == []

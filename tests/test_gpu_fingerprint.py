@@ -133,19 +133,9 @@ def test_hashes_dense_synthetic_peaks(engine, oracle):
 
 
 def explain_peak_diffs(oracle_mod, S_ref, S_gpu, pk_ref, pk_gpu):
-    """Every peak present on one side only must be a near-tie: within tolerance of its neighbourhood maximum
-    on the side that rejected it."""
-    from scipy.ndimage import maximum_filter
-    only = np.setxor1d(pk_ref, pk_gpu)
-    M_ref = maximum_filter(S_ref, size=(25, 103), mode="constant", cval=-1)
-    M_gpu = maximum_filter(S_gpu, size=(25, 103), mode="constant", cval=-1)
-    for k in only:
-        t, f = int(k >> 9), int(k & 511)
-        for S, M in ((S_ref, M_ref), (S_gpu, M_gpu)):
-            gap = M[t, f] - S[t, f]
-            thr_gap = abs(S[t, f] - 0.001)
-            assert gap <= 2 * TOL * max(abs(M[t, f]), 1.0) or thr_gap <= 2 * TOL, (t, f, gap)
-    return len(only)
+    """Every peak present on one side only must be a near-tie (oracle/parity.py, shared with bench.py's parity leg)."""
+    from oracle import parity
+    return parity.explain_peak_diffs(S_ref, S_gpu, pk_ref, pk_gpu)
 
 
 def test_end_to_end_fingerprint_10s(engine, oracle, clip10):

@@ -196,3 +196,35 @@ def test_deleted_track_disappears_and_only_it(oracle):
     one = ix.match(*q, tombstone=tomb)
     assert int(one["track"][0]) == 4 and 1 not in one["track"]
     assert np.array_equal(one, both[both["track"] != 1])
+
+
+def test_f32_streaming_baseline_follows_the_specification(oracle):
+    """oracle/aid_cpu_f32.c (the CPU baseline bench.py states): spectrogram within AID_SPEC_TOL of the double-precision
+    checker, peaks exactly aid_oracle_peaks of its OWN spectrogram (streaming ring == full-spectrogram definition),
+    hashes by the shared hasher; ragged batch, short and edge lengths included."""
+    from audio_ident_b200 import synth
+    clips = [synth.make_track(40 + k, s) for k, s in enumerate([12.0, 0.064, 0.07, 1.0, 2.1, 3.3, 0.0])]
+    clips.append(np.zeros(5000, np.float32))                    # silence: no peaks
+    clips.append(np.tile(np.r_[1.0, np.zeros(127)], 80).astype(np.float32))      # impulse train: tie-heavy rows
+    for x in clips:
+        S, F = oracle.stft(x), oracle.stft_f32(x)
+        assert S.shape == F.shape
+        if S.size:
+            assert (np.abs(F - S) <= 1e-4 * np.maximum(np.abs(S), 1.0)).all()
+        try:
+            ref = oracle.peaks(F)
+        except OverflowError:
+            with pytest.raises(OverflowError):
+                oracle.peaks_f32(x)
+            continue
+        assert np.array_equal(oracle.peaks_f32(x), ref)
+    pcm = np.concatenate(clips[:7])
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clips[:7]])])
+    h, t, hoff, nh, npk, used = oracle.fingerprint_batch(pcm, off, 2, f32=True)
+    for i, x in enumerate(clips[:7]):
+        rh, rt = oracle.hashes(oracle.peaks_f32(x))
+        assert np.array_equal(h[hoff[i]:hoff[i + 1]], rh) and np.array_equal(t[hoff[i]:hoff[i + 1]], rt)
+    # and against the checker end to end: same hashes unless a float near-tie peak flips
+    h64, t64, hoff64, *_ = oracle.fingerprint_batch(pcm, off, 2)
+    same = sum(np.array_equal(h[hoff[i]:hoff[i + 1]], h64[hoff64[i]:hoff64[i + 1]]) for i in range(7))
+    assert same >= 6
