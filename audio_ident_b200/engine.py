@@ -353,6 +353,15 @@ class Engine:
         self._check(self._L.aid_match_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return int(out[0]), int(out[1])
 
+    # -- decode feed ---------------------------------------------------------------------------
+    def resample_48k_to_16k(self, pcm48) -> np.ndarray:
+        """float32 48 kHz mono -> float32 16 kHz mono (61-tap zero-phase polyphase decimator on the GPU)."""
+        x = np.frombuffer(pcm48, dtype="<f4") if isinstance(pcm48, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(pcm48, np.float32)
+        out = np.empty(int(self._L.aid_resample_out_len(len(x))), np.float32)
+        self._check(self._L.aid_resample_48k_to_16k_host(self._h, _ptr(x), len(x), _ptr(out)))
+        return out
+
     def copy_device(self, d_dst, d_src, nbytes: int, stream=None) -> None:
         self._check(self._L.aid_copy_device(self._h, _ptr(d_dst), _ptr(d_src), int(nbytes), _ptr(stream)))
 

@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 mkdir -p ../../build/obj
 objs=""
 pids=""
-for f in stft peaks scan hasher synth index match exchange dedup engine; do
+for f in stft peaks scan hasher synth index match exchange dedup resample engine; do
   [ -f $f.cu ] || continue
   o=../../build/obj/$f.o
   if [ ! -f $o ] || [ $f.cu -nt $o ] || [ common.cuh -nt $o ] || [ engine.h -nt $o ] || [ index.h -nt $o ] || [ ../../include/aid_params.h -nt $o ] || [ ../../include/audio_ident_b200.h -nt $o ]; then

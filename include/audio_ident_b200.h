@@ -271,6 +271,17 @@ int aid_dedup_scan(aid_dedup* d, const uint32_t* q_words, const int64_t* q_off /
 /* device time of the last scan's kernels (CUDA events on the store's stream), milliseconds */
 double      aid_dedup_last_scan_ms(const aid_dedup* d);
 
+/* ---- decode feed -------------------------------------------------------------
+ * The reference's decode_dual_rate starts two ffmpeg children per file, one per output rate
+ * (audio-ident-service/app/audio/decode.py:74-87, :37-58). With these entry points one 48 kHz decode is enough:
+ * the 16 kHz stream of the fingerprint path is derived on the GPU by a 61-tap zero-phase polyphase decimator,
+ * y[j] = sum_{m=-30..30} h[m+30] x[3j+m] (x = 0 outside the clip), h = firwin(61, 1/3, kaiser 5.0) -- the design of
+ * scipy.signal.resample_poly(x, 1, 3), which is the oracle. Not bit-compatible with ffmpeg's own resampler. */
+int64_t aid_resample_out_len(int64_t n_in);                 /* ceil(n_in / 3) */
+void    aid_resample_taps(float* taps /* [61] */);          /* the float32 filter both sides use */
+int     aid_resample_48k_to_16k_host(aid_engine* e, const float* pcm48, int64_t n_in, float* pcm16);
+int     aid_resample_48k_to_16k_dev(aid_engine* e, const float* d_in, int64_t n_in, float* d_out, void* stream);
+
 /* ---- helpers for bindings that do not link the CUDA runtime themselves ---------------------- */
 int aid_device_alloc(aid_engine* e, int64_t bytes, void** d_ptr);
 int aid_device_free(aid_engine* e, void* d_ptr);

@@ -65,3 +65,21 @@ def match(ix_hash, ix_track, ix_t, q_hash, q_t):
     rows = [(len(v), k[0], k[1], min(v), max(v)) for k, v in votes.items() if len(v) >= MIN_VOTES]
     rows.sort(key=lambda r: (-r[0], r[1], r[2]))
     return rows[:MAX_ROWS]
+
+
+# ---------------------------------------------------------------- decode feed (csrc/resample.cu)
+def resample_taps() -> np.ndarray:
+    """firwin(61, 1/3, window=("kaiser", 5.0)) in double: the default design of scipy.signal.resample_poly(x, 1, 3)."""
+    from scipy.signal import firwin
+    return firwin(61, 1.0 / 3.0, window=("kaiser", 5.0))
+
+
+def resample3(x: np.ndarray) -> np.ndarray:
+    """y[j] = sum_m h[m + 30] x[3 j + m], zero outside the clip, j < ceil(n / 3) -- in double, with the float32 taps
+    the engine uses (what csrc/resample.cu must reproduce); scipy.signal.resample_poly(x, 1, 3) is the same up to the
+    rounding of the taps (tests/test_oracle.py)."""
+    x = np.asarray(x, np.float64)
+    h = resample_taps().astype(np.float32).astype(np.float64)
+    full = np.convolve(x, h)                      # full[i] = sum_k h[k] x[i - k]; y[j] = full[3 j + 30]
+    n_out = (len(x) + 2) // 3
+    return full[30:30 + 3 * n_out:3][:n_out]

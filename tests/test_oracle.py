@@ -228,3 +228,25 @@ def test_f32_streaming_baseline_follows_the_specification(oracle):
     h64, t64, hoff64, *_ = oracle.fingerprint_batch(pcm, off, 2)
     same = sum(np.array_equal(h[hoff[i]:hoff[i + 1]], h64[hoff64[i]:hoff64[i + 1]]) for i in range(7))
     assert same >= 6
+
+
+def test_resampler_definition_matches_scipy_resample_poly():
+    """the decimator's definition (oracle/np_oracle.py resample3, what csrc/resample.cu
+    implements) is scipy.signal.resample_poly(x, 1, 3); the engine's float32 tap table is scipy's firwin design."""
+    import ctypes as C
+    from scipy.signal import resample_poly
+    from audio_ident_b200 import _lib
+    L = _lib.load()
+    taps = np.zeros(61, np.float32)
+    L.aid_resample_taps(taps.ctypes.data_as(C.POINTER(C.c_float)))
+    ref = npo.resample_taps()
+    assert np.abs(taps - ref).max() < 2e-8 and abs(float(taps.astype(np.float64).sum()) - 1.0) < 1e-6
+    assert np.array_equal(taps, taps[::-1])                      # linear phase
+    assert [L.aid_resample_out_len(n) for n in (0, 1, 2, 3, 4, 48000)] == [0, 1, 1, 1, 2, 16000]
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 59, 61, 1000, 48001):
+        x = rng.uniform(-1, 1, n)
+        y = npo.resample3(x)
+        z = resample_poly(x, 1, 3)
+        assert y.shape == z.shape
+        assert np.abs(y - z).max() < 1e-6
