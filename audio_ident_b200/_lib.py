@@ -77,6 +77,7 @@ def load() -> C.CDLL:
         "aid_index_load": (C.c_int, [vp, C.c_char_p]),
         "aid_query_host": (C.c_int, [vp, vp, i64p, C.c_int, vp, C.c_int, i32p]),
         "aid_query_dev": (C.c_int, [vp, vp, i64p, C.c_int, vp, C.c_int, i32p]),
+        "aid_query_windows_host": (C.c_int, [vp, vp, i64p, i64p, C.c_int, vp, C.c_int, i32p]),
         "aid_query_hashes": (C.c_int, [vp, vp, vp, i64p, C.c_int, vp, C.c_int, i32p]),
         "aid_match_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp]),
         "aid_copy_device": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
@@ -90,6 +91,10 @@ def load() -> C.CDLL:
         "aid_match_exchange_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int64, vp, C.c_int, vp, vp]),
         "aid_identify_exchange_dev": (C.c_int, [vp, vp, vp, i64p, C.c_int, vp, C.c_int64, vp, C.c_int, vp, vp]),
         "aid_identify_exchange_host": (C.c_int, [vp, vp, vp, i64p, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int, vp]),
+        "aid_identify_exchange_windows_dev": (C.c_int, [vp, vp, vp, i64p, i64p, C.c_int, vp, C.c_int64, vp, C.c_int, vp, vp]),
+        "aid_identify_exchange_windows_host": (C.c_int, [vp, vp, vp, i64p, i64p, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp, C.c_int, vp]),
+        "aid_fingerprint_windows_dev": (C.c_int, [vp, vp, i64p, i64p, C.c_int, C.POINTER(FpDeviceResult), vp]),
+        "aid_synth_tracks_strided_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_uint64, vp]),
         "aid_match_stats": (C.c_int, [vp, i64p]),
         "aid_resample_out_len": (C.c_int64, [C.c_int64]),
         "aid_resample_taps": (None, [f32p]),
@@ -132,10 +137,11 @@ EXPORTED = [  # every symbol include/audio_ident_b200.h declares (tests/test_abi
     "aid_engine_set_max_batch_frames", "aid_engine_set_stage_timing", "aid_engine_stage_times", "aid_fingerprint_host", "aid_fingerprint_dev", "aid_stft_host",
     "aid_peaks_host", "aid_hashes_host", "aid_num_frames", "aid_index_add_host", "aid_index_add_host_fp", "aid_index_add_dev",
     "aid_index_add_hashes", "aid_index_delete", "aid_index_commit", "aid_index_clear", "aid_index_set_grouping", "aid_index_stats",
-    "aid_index_track_name", "aid_index_save", "aid_index_load", "aid_query_host", "aid_query_dev",
+    "aid_index_track_name", "aid_index_save", "aid_index_load", "aid_query_host", "aid_query_dev", "aid_query_windows_host",
     "aid_query_hashes", "aid_match_dev", "aid_exchange_create", "aid_exchange_destroy", "aid_exchange_handle",
     "aid_exchange_connect", "aid_exchange_connect_local", "aid_exchange_set_timeout_ms", "aid_exchange_status",
-    "aid_match_exchange_dev", "aid_identify_exchange_dev", "aid_identify_exchange_host", "aid_match_stats", "aid_resample_out_len", "aid_resample_taps",
+    "aid_match_exchange_dev", "aid_identify_exchange_dev", "aid_identify_exchange_host", "aid_identify_exchange_windows_dev", "aid_identify_exchange_windows_host",
+    "aid_fingerprint_windows_dev", "aid_synth_tracks_strided_dev", "aid_match_stats", "aid_resample_out_len", "aid_resample_taps",
     "aid_resample_48k_to_16k_host", "aid_resample_48k_to_16k_dev", "aid_copy_device", "aid_device_alloc", "aid_device_free", "aid_copy_to_device", "aid_copy_to_host",
     "aid_synth_tracks_dev", "aid_dedup_create", "aid_dedup_destroy", "aid_dedup_last_error", "aid_dedup_size",
     "aid_dedup_launch_count", "aid_dedup_add", "aid_dedup_scan", "aid_dedup_last_scan_ms",

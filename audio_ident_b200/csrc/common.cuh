@@ -104,4 +104,4 @@ cudaError_t aid_launch_hash_write(const uint32_t* d_peaks, const uint32_t* d_pea
 cudaError_t aid_launch_gather_u32(const uint32_t* d_src, const uint32_t* d_idx, uint32_t* d_dst, int n,
                                   cudaStream_t st);
 cudaError_t aid_launch_synth(float* d_pcm, int64_t first_track, int n_tracks, int64_t samples_per_track,
-                             uint64_t seed, cudaStream_t st);
+                             uint64_t seed, cudaStream_t st, int64_t track_stride = 1);

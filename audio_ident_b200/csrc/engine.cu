@@ -124,23 +124,30 @@ extern "C" int aid_engine_set_max_batch_frames(aid_engine* e, int64_t frames) {
 // Tracks [first, first+count) of a ragged batch. Tracks longer than frame_limit frames are planned
 // with zero frames and flagged AID_TRACK_TOO_LONG.
 int aid_build_plan(const int64_t* sample_off, int first, int count, int64_t frame_limit, Plan& plan) {
+    return aid_build_plan_windows(sample_off + first, sample_off + first + 1, count, sample_off[first], frame_limit, plan);
+}
+
+// General form: track / window i is pcm[begin[i] .. end[i]) -- the ranges may overlap (the three sub-windows of a 5 s
+// query clip, the sliding windows of a long recording) or leave gaps; pcm_begin of a unit is relative to `base`, the
+// sample the caller's device pointer stands on.
+int aid_build_plan_windows(const int64_t* begin_of, const int64_t* end_of, int count, int64_t base, int64_t frame_limit,
+                           Plan& plan) {
     plan = Plan();
     plan.n_tracks = count;
     plan.frames.resize(count);
     plan.frame_off.assign(count + 1, 0);
     plan.host_status.assign(count, AID_TRACK_OK);
     plan.first_punit.assign(count + 1, 0);
-    const int64_t base = sample_off[first];
     // blocks streamed back to back by one warp of the peak kernel: longer runs re-read fewer halo rows, but the
     // launch needs several waves of warps (148 SMs x 16 resident warps) to balance
     int64_t all_blocks = 0;
     for (int i = 0; i < count; i++) {
-        const int64_t T = aid_num_frames(sample_off[first + i + 1] - sample_off[first + i]);
+        const int64_t T = aid_num_frames(end_of[i] - begin_of[i]);
         if (T <= frame_limit) all_blocks += (T + AID_PEAK_BLOCK_FRAMES - 1) / AID_PEAK_BLOCK_FRAMES;
     }
     const int64_t run_blocks = std::max<int64_t>(1, std::min<int64_t>(AID_PEAK_RUN_BLOCKS, all_blocks / (8 * 148 * 16)));
     for (int i = 0; i < count; i++) {
-        const int64_t begin = sample_off[first + i], end = sample_off[first + i + 1];
+        const int64_t begin = begin_of[i], end = end_of[i];
         if (end < begin) return AID_E_ARG;
         int64_t T = aid_num_frames(end - begin);
         if (T == 0) plan.host_status[i] |= AID_TRACK_EMPTY;
@@ -286,18 +293,23 @@ int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d
 }
 
 // ------------------------------------------------------------------------- fingerprint entry points
-extern "C" int aid_fingerprint_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_tracks,
-                                   aid_fp_device_result* out, void* stream) {
-    if (!e || !sample_off || !out || n_tracks < 0 || (!d_pcm && n_tracks > 0 && sample_off[n_tracks] > sample_off[0]))
-        return AID_E_ARG;
+// d_pcm points at sample `base`; window i is samples [win_begin[i], win_end[i]) of that numbering (overlaps allowed)
+static int fingerprint_windows_dev(aid_engine* e, const float* d_pcm, int64_t base, const int64_t* win_begin,
+                                   const int64_t* win_end, int n_tracks, aid_fp_device_result* out, void* stream);
+int aid_fingerprint_windows_core(aid_engine* e, const float* d_pcm, int64_t base, const int64_t* win_begin,
+                                 const int64_t* win_end, int n, aid_fp_device_result* out, void* stream) {
+    return fingerprint_windows_dev(e, d_pcm, base, win_begin, win_end, n, out, stream);
+}
+static int fingerprint_windows_dev(aid_engine* e, const float* d_pcm, int64_t base, const int64_t* win_begin,
+                                   const int64_t* win_end, int n_tracks, aid_fp_device_result* out, void* stream) {
     AID_CUDA(e, cudaSetDevice(e->device));
     Slot& s = e->slot[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.st;
     Plan plan;
-    int rc = aid_build_plan(sample_off, 0, n_tracks, AID_MAX_FRAMES, plan);
+    int rc = aid_build_plan_windows(win_begin, win_end, n_tracks, base, AID_MAX_FRAMES, plan);
     if (rc != AID_OK) return rc;
     if ((rc = aid_slot_prepare(e, s, plan, false, 0)) != AID_OK) return rc;
-    if ((rc = aid_run_fingerprint(e, s, plan, d_pcm + sample_off[0], st)) != AID_OK) return rc;
+    if ((rc = aid_run_fingerprint(e, s, plan, d_pcm, st)) != AID_OK) return rc;
     // host-known status bits (empty / too long) are OR-ed in on the device so d_status is complete
     bool any = false;
     for (int32_t v : plan.host_status) any |= v != 0;
@@ -317,6 +329,20 @@ extern "C" int aid_fingerprint_dev(aid_engine* e, const float* d_pcm, const int6
     out->d_spec = s.spec.as<float>();
     out->total_frames = plan.total_frames;
     return AID_OK;
+}
+
+extern "C" int aid_fingerprint_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_tracks,
+                                   aid_fp_device_result* out, void* stream) {
+    if (!e || !sample_off || !out || n_tracks < 0 || (!d_pcm && n_tracks > 0 && sample_off[n_tracks] > sample_off[0]))
+        return AID_E_ARG;
+    return fingerprint_windows_dev(e, d_pcm + sample_off[0], sample_off[0], sample_off, sample_off + 1, n_tracks, out, stream);
+}
+
+extern "C" int aid_fingerprint_windows_dev(aid_engine* e, const float* d_pcm, const int64_t* win_begin, const int64_t* win_end,
+                                           int n_windows, aid_fp_device_result* out, void* stream) {
+    if (!e || !out || n_windows < 0 || (n_windows > 0 && (!win_begin || !win_end || !d_pcm))) return AID_E_ARG;
+    for (int i = 0; i < n_windows; i++) if (win_begin[i] < 0 || win_end[i] < win_begin[i]) return AID_E_ARG;
+    return fingerprint_windows_dev(e, d_pcm, 0, win_begin, win_end, n_windows, out, stream);
 }
 
 namespace {
@@ -586,12 +612,16 @@ extern "C" int aid_copy_to_host(aid_engine* e, void* h_dst, const void* d_src, i
     AID_CUDA(e, cudaMemcpy(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
     return AID_OK;
 }
-extern "C" int aid_synth_tracks_dev(aid_engine* e, float* d_pcm, int64_t first_track, int n_tracks,
-                                    int64_t samples_per_track, uint64_t seed, void* stream) {
-    if (!e || (!d_pcm && n_tracks > 0) || n_tracks < 0 || samples_per_track < 0) return AID_E_ARG;
+extern "C" int aid_synth_tracks_strided_dev(aid_engine* e, float* d_pcm, int64_t first_track, int64_t track_stride,
+                                            int n_tracks, int64_t samples_per_track, uint64_t seed, void* stream) {
+    if (!e || (!d_pcm && n_tracks > 0) || n_tracks < 0 || samples_per_track < 0 || track_stride < 1) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : e->slot[0].st;
-    AID_CUDA(e, aid_launch_synth(d_pcm, first_track, n_tracks, samples_per_track, seed, st));
+    AID_CUDA(e, aid_launch_synth(d_pcm, first_track, n_tracks, samples_per_track, seed, st, track_stride));
     e->launches += (n_tracks + 32767) / 32768;
     return AID_OK;
+}
+extern "C" int aid_synth_tracks_dev(aid_engine* e, float* d_pcm, int64_t first_track, int n_tracks,
+                                    int64_t samples_per_track, uint64_t seed, void* stream) {
+    return aid_synth_tracks_strided_dev(e, d_pcm, first_track, 1, n_tracks, samples_per_track, seed, stream);
 }

@@ -113,6 +113,8 @@ int aid_fail_cuda(aid_engine* e, cudaError_t ce, const char* what);
 #define AID_CUDA(e, call) do { cudaError_t ce_ = (call); if (ce_ != cudaSuccess) return aid_fail_cuda((e), ce_, #call); } while (0)
 
 int aid_build_plan(const int64_t* sample_off, int first, int count, int64_t frame_limit, Plan& plan);
+int aid_build_plan_windows(const int64_t* begin_of, const int64_t* end_of, int count, int64_t base, int64_t frame_limit,
+                           Plan& plan);
 // uploads descriptors, runs stft .. hashes on slot s for `plan`; d_pcm is the sub-batch's first sample.
 int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d_pcm, cudaStream_t st);
 int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, int64_t pcm_samples);

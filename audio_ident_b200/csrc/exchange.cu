@@ -19,6 +19,8 @@
 // rank, whose size needed a host synchronisation), k_wait_hashes holds the stream until all slices have arrived,
 // then probe/vote, the fused ranking + row stores, and the merge.
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include "engine.h"
 #include "index.h"
@@ -325,26 +327,26 @@ extern "C" int aid_match_exchange_dev(aid_engine* e, aid_exchange* x, const uint
                            n_map, d_rows, max_rows, d_n_rows, st);
 }
 
-extern "C" int aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const float* d_pcm, const int64_t* sample_off,
-                                         int n_windows, const uint32_t* d_track_map, int64_t n_map,
-                                         aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream) {
-    if (!e || !x || x->e != e || !x->connected || !sample_off || n_windows < 0 || n_windows > x->max_q || max_rows < 1 ||
-        max_rows > AID_MAX_ROWS || n_map < 0 || n_map >= ((int64_t)1 << 32)) return AID_E_ARG;
-    if (n_windows > 0 && (!d_rows || !d_n_rows)) return AID_E_ARG;
-    if (n_windows == 0) return AID_OK;
+int aid_fingerprint_windows_core(aid_engine* e, const float* d_pcm, int64_t base, const int64_t* win_begin,
+                                 const int64_t* win_end, int n, aid_fp_device_result* out, void* stream);   // engine.cu
+
+// The whole sharded step. d_pcm points at sample `base` of the caller's numbering; window i is samples
+// [win_begin[i], win_end[i]) of it -- windows may overlap (the three sub-windows of a 5 s clip, exact.py:48-52, or the
+// sliding windows of a long recording share their samples instead of being copied out three / two times).
+static int identify_core(aid_engine* e, aid_exchange* x, const float* d_pcm, int64_t base, const int64_t* win_begin,
+                         const int64_t* win_end, int n_windows, const uint32_t* d_track_map, int64_t n_map,
+                         aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, cudaStream_t st) {
     // A vote window is at most AID_QUERY_MAX_FRAMES frames (k_match packs t_query into 15 bits of the vote key and 16 bits
     // of q_first / q_last). Checked for ALL windows and before the epoch moves: every rank passes the same batch, so every
     // rank returns the same status and the ranks' epochs stay in step.
     for (int i = 0; i < n_windows; i++) {
-        if (sample_off[i + 1] < sample_off[i]) return AID_E_ARG;
-        if (aid_num_frames(sample_off[i + 1] - sample_off[i]) > AID_QUERY_MAX_FRAMES) return AID_E_TOO_LONG;
+        if (win_end[i] < win_begin[i]) return AID_E_ARG;
+        if (aid_num_frames(win_end[i] - win_begin[i]) > AID_QUERY_MAX_FRAMES) return AID_E_TOO_LONG;
     }
-    AID_CUDA(e, cudaSetDevice(e->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->slot[0].st;
     const int P = x->world, r = x->rank;
     const int lo = (int)((int64_t)r * n_windows / P), hi = (int)((int64_t)(r + 1) * n_windows / P);
     aid_fp_device_result fp{};
-    int rc = aid_fingerprint_dev(e, d_pcm, sample_off + lo, hi - lo, &fp, st);     // this rank's slice only
+    int rc = aid_fingerprint_windows_core(e, d_pcm, base, win_begin + lo, win_end + lo, hi - lo, &fp, st);     // this rank's slice only
     if (rc) return rc;
     const uint32_t epoch = ++x->epoch;
     const long long timeout_cycles = (long long)x->timeout_ms * x->clock_khz;
@@ -364,16 +366,45 @@ extern "C" int aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const f
                            d_n_rows, st);
 }
 
+static int identify_args_ok(aid_engine* e, aid_exchange* x, int n_windows, int max_rows, int64_t n_map) {
+    return e && x && x->e == e && x->connected && n_windows >= 0 && n_windows <= x->max_q && max_rows >= 1 &&
+           max_rows <= AID_MAX_ROWS && n_map >= 0 && n_map < ((int64_t)1 << 32);
+}
+
+extern "C" int aid_identify_exchange_dev(aid_engine* e, aid_exchange* x, const float* d_pcm, const int64_t* sample_off,
+                                         int n_windows, const uint32_t* d_track_map, int64_t n_map,
+                                         aid_match_row* d_rows, int max_rows, int32_t* d_n_rows, void* stream) {
+    if (!identify_args_ok(e, x, n_windows, max_rows, n_map) || !sample_off) return AID_E_ARG;
+    if (n_windows > 0 && (!d_rows || !d_n_rows)) return AID_E_ARG;
+    if (n_windows == 0) return AID_OK;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    return identify_core(e, x, d_pcm, 0, sample_off, sample_off + 1, n_windows, d_track_map, n_map, d_rows, max_rows, d_n_rows,
+                         stream ? (cudaStream_t)stream : e->slot[0].st);
+}
+
+extern "C" int aid_identify_exchange_windows_dev(aid_engine* e, aid_exchange* x, const float* d_pcm, const int64_t* win_begin,
+                                                 const int64_t* win_end, int n_windows, const uint32_t* d_track_map,
+                                                 int64_t n_map, aid_match_row* d_rows, int max_rows, int32_t* d_n_rows,
+                                                 void* stream) {
+    if (!identify_args_ok(e, x, n_windows, max_rows, n_map)) return AID_E_ARG;
+    if (n_windows > 0 && (!d_rows || !d_n_rows || !win_begin || !win_end)) return AID_E_ARG;
+    if (n_windows == 0) return AID_OK;
+    for (int i = 0; i < n_windows; i++) if (win_begin[i] < 0) return AID_E_ARG;
+    AID_CUDA(e, cudaSetDevice(e->device));
+    return identify_core(e, x, d_pcm, 0, win_begin, win_end, n_windows, d_track_map, n_map, d_rows, max_rows, d_n_rows,
+                         stream ? (cudaStream_t)stream : e->slot[0].st);
+}
+
 // Host buffers in, host buffers out: what a service process hands over (the windows' PCM in pinned or pageable host
-// memory) and what it gets back (rows of its own slice of the batch, or of all windows). Rank r only needs the PCM of
-// windows [r*n/P, (r+1)*n/P) on its device, so that is all that crosses PCIe; the merged rows of every window end up on
-// every rank and `rows_first / rows_count` says which of them this caller wants copied back.
-extern "C" int aid_identify_exchange_host(aid_engine* e, aid_exchange* x, const float* pcm, const int64_t* sample_off,
-                                          int n_windows, const uint32_t* d_track_map, int64_t n_map,
-                                          int rows_first, int rows_count, aid_match_row* rows, int max_rows,
-                                          int32_t* n_rows) {
-    if (!e || !x || x->e != e || !sample_off || n_windows < 0 || rows_first < 0 || rows_count < 0 ||
-        rows_first + (int64_t)rows_count > n_windows || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
+// memory) and what it gets back (rows of its own slice of the batch, or of all windows). Rank r only needs the samples
+// its windows [r*n/P, (r+1)*n/P) cover, so that span is all that crosses PCIe -- once, however much the windows
+// overlap; the merged rows of every window end up on every rank and `rows_first / rows_count` says which of them this
+// caller wants copied back.
+static int identify_host(aid_engine* e, aid_exchange* x, const float* pcm, const int64_t* win_begin, const int64_t* win_end,
+                         int n_windows, const uint32_t* d_track_map, int64_t n_map, int rows_first, int rows_count,
+                         aid_match_row* rows, int max_rows, int32_t* n_rows) {
+    if (!identify_args_ok(e, x, n_windows, max_rows, n_map) || rows_first < 0 || rows_count < 0 ||
+        rows_first + (int64_t)rows_count > n_windows) return AID_E_ARG;
     if (rows_count > 0 && (!rows || !n_rows)) return AID_E_ARG;
     if (n_windows == 0) return AID_OK;
     AID_CUDA(e, cudaSetDevice(e->device));
@@ -381,16 +412,18 @@ extern "C" int aid_identify_exchange_host(aid_engine* e, aid_exchange* x, const 
     Index* ix = e->index;
     const int P = x->world, r = x->rank;
     const int lo = (int)((int64_t)r * n_windows / P), hi = (int)((int64_t)(r + 1) * n_windows / P);
-    const int64_t s0 = sample_off[lo], samples = sample_off[hi] - s0;
+    int64_t s0 = INT64_MAX, s1 = INT64_MIN;
+    for (int i = lo; i < hi; i++) { s0 = std::min(s0, win_begin[i]); s1 = std::max(s1, win_end[i]); }
+    const int64_t samples = hi > lo ? s1 - s0 : 0;
+    if (hi <= lo) s0 = 0;
     if (samples < 0 || (samples > 0 && !pcm)) return AID_E_ARG;
     AID_CUDA(e, s.pcm.ensure((size_t)std::max<int64_t>(samples, 1) * sizeof(float)));
     AID_CUDA(e, ix->rows.ensure((size_t)n_windows * max_rows * sizeof(aid_match_row)));
     AID_CUDA(e, ix->rows_n.ensure((size_t)n_windows * 4));
     if (samples > 0)
         AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + s0, (size_t)samples * sizeof(float), cudaMemcpyHostToDevice, s.st));
-    // the device entry point indexes d_pcm with the batch's sample offsets: shift the base so that sample s0 is s.pcm[0]
-    int rc = aid_identify_exchange_dev(e, x, s.pcm.as<float>() - s0, sample_off, n_windows, d_track_map, n_map,
-                                       ix->rows.as<aid_match_row>(), max_rows, ix->rows_n.as<int32_t>(), s.st);
+    int rc = identify_core(e, x, s.pcm.as<float>(), s0, win_begin, win_end, n_windows, d_track_map, n_map,
+                           ix->rows.as<aid_match_row>(), max_rows, ix->rows_n.as<int32_t>(), s.st);
     if (rc) return rc;
     if (rows_count > 0) {
         AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.as<aid_match_row>() + (int64_t)rows_first * max_rows,
@@ -400,4 +433,23 @@ extern "C" int aid_identify_exchange_host(aid_engine* e, aid_exchange* x, const 
     AID_CUDA(e, cudaStreamSynchronize(s.st));
     for (int i = 0; i < rows_count; i++) if (n_rows[i] < 0) return AID_E_TIMEOUT;
     return AID_OK;
+}
+
+extern "C" int aid_identify_exchange_host(aid_engine* e, aid_exchange* x, const float* pcm, const int64_t* sample_off,
+                                          int n_windows, const uint32_t* d_track_map, int64_t n_map,
+                                          int rows_first, int rows_count, aid_match_row* rows, int max_rows,
+                                          int32_t* n_rows) {
+    if (!sample_off) return AID_E_ARG;
+    return identify_host(e, x, pcm, sample_off, sample_off + 1, n_windows, d_track_map, n_map, rows_first, rows_count, rows,
+                         max_rows, n_rows);
+}
+
+extern "C" int aid_identify_exchange_windows_host(aid_engine* e, aid_exchange* x, const float* pcm, const int64_t* win_begin,
+                                                  const int64_t* win_end, int n_windows, const uint32_t* d_track_map,
+                                                  int64_t n_map, int rows_first, int rows_count, aid_match_row* rows,
+                                                  int max_rows, int32_t* n_rows) {
+    if (n_windows > 0 && (!win_begin || !win_end)) return AID_E_ARG;
+    for (int i = 0; i < n_windows; i++) if (win_begin[i] < 0) return AID_E_ARG;
+    return identify_host(e, x, pcm, win_begin, win_end, n_windows, d_track_map, n_map, rows_first, rows_count, rows, max_rows,
+                         n_rows);
 }

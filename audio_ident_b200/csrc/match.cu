@@ -23,6 +23,8 @@
 //   partial counts ever need adding) and writes the final rows.
 // HBM traffic per query window: one table / directory entry per hash and 4 B per posting touched, random access.
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include "engine.h"
 #include "index.h"
 
@@ -492,29 +494,34 @@ extern "C" int aid_copy_device(aid_engine* e, void* d_dst, const void* d_src, in
     return AID_OK;
 }
 
-static int query_pcm(aid_engine* e, const float* pcm, bool on_device, const int64_t* sample_off, int n_q,
+// window q is pcm[win_begin[q] .. win_end[q]); windows may overlap (then a sub-batch uploads the span they cover once)
+static int query_pcm(aid_engine* e, const float* pcm, bool on_device, const int64_t* win_begin, const int64_t* win_end, int n_q,
                      aid_match_row* rows, int max_rows, int32_t* n_rows) {
-    if (!e || !sample_off || !rows || !n_rows || n_q < 0 || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
-    if (n_q > 0 && !pcm && sample_off[n_q] > sample_off[0]) return AID_E_ARG;
+    if (!e || !win_begin || !win_end || !rows || !n_rows || n_q < 0 || max_rows < 1 || max_rows > AID_MAX_ROWS) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
-    for (int i = 0; i < n_q; i++)
-        if (aid_num_frames(sample_off[i + 1] - sample_off[i]) > AID_QUERY_MAX_FRAMES) return AID_E_TOO_LONG;
+    for (int i = 0; i < n_q; i++) {
+        if (win_begin[i] < 0 || win_end[i] < win_begin[i] || (!pcm && win_end[i] > win_begin[i])) return AID_E_ARG;
+        if (aid_num_frames(win_end[i] - win_begin[i]) > AID_QUERY_MAX_FRAMES) return AID_E_TOO_LONG;
+    }
     Slot& s = e->slot[0];
     for (int first = 0; first < n_q;) {
         int64_t frames = 0; int count = 0;
+        int64_t s0 = INT64_MAX, s1 = INT64_MIN;
         while (first + count < n_q) {
-            const int64_t T = aid_num_frames(sample_off[first + count + 1] - sample_off[first + count]);
+            const int64_t T = aid_num_frames(win_end[first + count] - win_begin[first + count]);
             if (count > 0 && frames + T > e->max_batch_frames) break;
-            frames += T; count++;
+            frames += T;
+            s0 = std::min(s0, win_begin[first + count]); s1 = std::max(s1, win_end[first + count]);
+            count++;
         }
         Plan plan;
-        int rc = aid_build_plan(sample_off, first, count, AID_QUERY_MAX_FRAMES, plan);
+        int rc = aid_build_plan_windows(win_begin + first, win_end + first, count, s0, AID_QUERY_MAX_FRAMES, plan);
         if (rc) return rc;
-        const int64_t samples = sample_off[first + count] - sample_off[first];
+        const int64_t samples = s1 - s0;
         if ((rc = aid_slot_prepare(e, s, plan, !on_device, samples))) return rc;
-        const float* d_pcm = pcm + sample_off[first];
+        const float* d_pcm = pcm + s0;
         if (!on_device) {
-            if (samples > 0) AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + sample_off[first], (size_t)samples * 4, cudaMemcpyHostToDevice, s.st));
+            if (samples > 0) AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + s0, (size_t)samples * 4, cudaMemcpyHostToDevice, s.st));
             d_pcm = s.pcm.as<float>();
         }
         if ((rc = aid_run_fingerprint(e, s, plan, d_pcm, s.st))) return rc;
@@ -527,11 +534,17 @@ static int query_pcm(aid_engine* e, const float* pcm, bool on_device, const int6
 
 extern "C" int aid_query_host(aid_engine* e, const float* pcm, const int64_t* sample_off, int n_queries,
                               aid_match_row* rows, int max_rows, int32_t* n_rows) {
-    return query_pcm(e, pcm, false, sample_off, n_queries, rows, max_rows, n_rows);
+    if (!sample_off) return AID_E_ARG;
+    return query_pcm(e, pcm, false, sample_off, sample_off + 1, n_queries, rows, max_rows, n_rows);
 }
 extern "C" int aid_query_dev(aid_engine* e, const float* d_pcm, const int64_t* sample_off, int n_queries,
                              aid_match_row* rows, int max_rows, int32_t* n_rows) {
-    return query_pcm(e, d_pcm, true, sample_off, n_queries, rows, max_rows, n_rows);
+    if (!sample_off) return AID_E_ARG;
+    return query_pcm(e, d_pcm, true, sample_off, sample_off + 1, n_queries, rows, max_rows, n_rows);
+}
+extern "C" int aid_query_windows_host(aid_engine* e, const float* pcm, const int64_t* win_begin, const int64_t* win_end,
+                                      int n_windows, aid_match_row* rows, int max_rows, int32_t* n_rows) {
+    return query_pcm(e, pcm, false, win_begin, win_end, n_windows, rows, max_rows, n_rows);
 }
 
 extern "C" int aid_query_hashes(aid_engine* e, const uint32_t* hash, const uint32_t* t_anchor, const int64_t* hash_off,

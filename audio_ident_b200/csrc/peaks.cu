@@ -41,6 +41,7 @@ constexpr int kHalfF = AID_PEAK_HALF_F, kHalfT = AID_PEAK_HALF_T;
 // synchronisation at all; the layout [row][lane] makes every access conflict-free.
 struct WarpSmem {
     float A[kRing][32];        // group maximum; stored NEGATED when the group is a candidate (S >= 0, so the sign is free)
+                               // (the settlement reads other lanes' columns of it, behind a __syncwarp)
     float C5[kRing][32];
     uint32_t buf[kBuf];
 };
@@ -231,7 +232,9 @@ __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int 
         const float ml = __shfl_up_sync(AID_FULL_MASK, ma, 3), mr = __shfl_down_sync(AID_FULL_MASK, ma, 3);
         keep &= (ml <= v ? 0x000fu : 0u) | 0x0ff0u | (mr <= v ? 0xf000u : 0u);
     }
-    // settle survivors one at a time: one lane per window row
+    // settle survivors one at a time: one lane per window row (the lanes read each other's A columns: make the ring
+    // writes of this trip visible first)
+    __syncwarp();
     for (;;) {
         const uint32_t who = __ballot_sync(AID_FULL_MASK, keep != 0);
         if (!who) break;
@@ -242,7 +245,18 @@ __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int 
         if (lane == src) keep &= keep - 1;
         const int rw = c - kHalfT + lane;
         bool ok = true;
-        if (lane <= 2 * kHalfT && rw >= 0 && rw < st.T) ok = edges_le(st.base + (int64_t)rw * AID_NBINS, f, vv);
+        if (lane <= 2 * kHalfT && rw >= 0 && rw < st.T) {
+            // The edge bins of this row lie inside two aligned groups whose maxima are still in the A ring: if neither
+            // exceeds the candidate, the row is settled without touching global memory (the usual case -- the
+            // candidate is the maximum of 80 bins x 25 rows). Only rows where an edge group holds something larger
+            // are re-read and tested bin by bin. (This removed most of the kernel's DRAM traffic above the algorithmic
+            // bytes: by now the rows have left the L2, profiles/r02_peaks.md.)
+            const int i = f & 15, g = f >> 4;
+            const int gl = (i <= 3 ? g - 3 : g - 2) - 1, gr = i >= 12 ? g + 4 : g + 3;
+            const float* arow = sm.A[rw & (kRing - 1)];
+            const float el = gl >= 0 ? fabsf(arow[gl]) : -1.0f, er = gr <= 31 ? fabsf(arow[gr]) : -1.0f;
+            if (fmaxf(el, er) > vv) ok = edges_le(st.base + (int64_t)rw * AID_NBINS, f, vv);
+        }
         if (__all_sync(AID_FULL_MASK, ok)) {
             const uint32_t e = ((uint32_t)c << AID_PEAK_F_BITS) | (uint32_t)f;
             if (lane == 0) {

@@ -26,9 +26,9 @@ __device__ __forceinline__ float u01(uint64_t h) { return (float)(h >> 40) * (1.
 struct Burst { float centre, inv_sigma, omega, amp, phase, reach; };
 
 __global__ void __launch_bounds__(256)
-k_synth(float* __restrict__ pcm, int64_t first_track, int64_t samples_per_track, uint64_t seed) {
+k_synth(float* __restrict__ pcm, int64_t first_track, int64_t track_stride, int64_t samples_per_track, uint64_t seed) {
     __shared__ Burst s_b[kBursts];
-    const int64_t track = first_track + blockIdx.y;
+    const int64_t track = first_track + track_stride * blockIdx.y;
     const int cell = blockIdx.x;
     const uint64_t tkey = mix64(seed ^ mix64((uint64_t)track));
     if (threadIdx.x < kBursts) {
@@ -76,13 +76,13 @@ k_synth(float* __restrict__ pcm, int64_t first_track, int64_t samples_per_track,
 }  // namespace
 
 cudaError_t aid_launch_synth(float* d_pcm, int64_t first_track, int n_tracks, int64_t samples_per_track,
-                             uint64_t seed, cudaStream_t st) {
+                             uint64_t seed, cudaStream_t st, int64_t track_stride) {
     if (n_tracks <= 0 || samples_per_track <= 0) return cudaSuccess;
     const int cells = (int)((samples_per_track + kCell - 1) / kCell);
     for (int t0 = 0; t0 < n_tracks; t0 += 32768) {
         const int nt = n_tracks - t0 < 32768 ? n_tracks - t0 : 32768;
-        k_synth<<<dim3(cells, nt), 256, 0, st>>>(d_pcm + (int64_t)t0 * samples_per_track, first_track + t0,
-                                                 samples_per_track, seed);
+        k_synth<<<dim3(cells, nt), 256, 0, st>>>(d_pcm + (int64_t)t0 * samples_per_track, first_track + track_stride * t0,
+                                                 track_stride, samples_per_track, seed);
     }
     return cudaGetLastError();
 }

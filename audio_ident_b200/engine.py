@@ -162,6 +162,14 @@ class Engine:
                                                 _ptr(stream)))
         return res
 
+    def fingerprint_windows_dev(self, d_pcm, win_begin, win_end, stream=None) -> FpDeviceResult:
+        """fingerprint_dev for windows d_pcm[win_begin[i]:win_end[i]] that may overlap (no copies)."""
+        b, bp = self._off(win_begin)
+        e_, ep = self._off(win_end)
+        res = FpDeviceResult()
+        self._check(self._L.aid_fingerprint_windows_dev(self._h, _ptr(d_pcm), bp, ep, len(b), C.byref(res), _ptr(stream)))
+        return res
+
     def stft(self, pcm, sample_off) -> np.ndarray:
         sample_off, offp = self._off(sample_off)
         pcm = np.ascontiguousarray(pcm, np.float32)
@@ -295,6 +303,19 @@ class Engine:
         self._check(fn(self._h, _ptr(pcm), offp, n, rows.ctypes.data, max_rows, nr.ctypes.data_as(C.POINTER(C.c_int32))))
         return rows[:n], nr[:n]
 
+    def query_windows(self, pcm, win_begin, win_end, max_rows: int = MAX_ROWS):
+        """query() for windows pcm[win_begin[i]:win_end[i]] of a host array that may overlap: the span is uploaded once."""
+        b, bp = self._off(win_begin)
+        e_, ep = self._off(win_end)
+        n = len(b)
+        if isinstance(pcm, np.ndarray):
+            pcm = np.ascontiguousarray(pcm, np.float32)
+        rows = np.zeros((max(n, 1), max_rows), MATCH_ROW_DTYPE)
+        nr = np.zeros(max(n, 1), np.int32)
+        self._check(self._L.aid_query_windows_host(self._h, _ptr(pcm), bp, ep, n, rows.ctypes.data, max_rows,
+                                                   nr.ctypes.data_as(C.POINTER(C.c_int32))))
+        return rows[:n], nr[:n]
+
     def query_hashes(self, h, t, hash_off, max_rows: int = MAX_ROWS):
         hash_off, offp = self._off(hash_off)
         n = len(hash_off) - 1
@@ -331,6 +352,13 @@ class Engine:
                               max_rows: int = MAX_ROWS, stream=None) -> None:
         """The whole sharded identification step on the device (aid_identify_exchange_dev): this rank fingerprints
         its slice of the window batch, fingerprints and rows travel through the ranks' windows over NVLink."""
+        if isinstance(sample_off, tuple):                   # (win_begin, win_end): windows may overlap
+            b, bp = self._off(sample_off[0])
+            e_, ep = self._off(sample_off[1])
+            self._check(self._L.aid_identify_exchange_windows_dev(self._h, xchg._h, _ptr(d_pcm), bp, ep, len(b),
+                                                                  _ptr(d_track_map), int(n_map), _ptr(d_rows), int(max_rows),
+                                                                  _ptr(d_n_rows), _ptr(stream)))
+            return
         sample_off, offp = self._off(sample_off)
         self._check(self._L.aid_identify_exchange_dev(self._h, xchg._h, _ptr(d_pcm), offp, len(sample_off) - 1,
                                                       _ptr(d_track_map), int(n_map), _ptr(d_rows), int(max_rows),
@@ -341,6 +369,15 @@ class Engine:
                                max_rows: int = MAX_ROWS) -> None:
         """aid_identify_exchange_host: host window PCM in (only this rank's slice crosses PCIe), merged rows of windows
         [rows_first, rows_first + rows_count) back in the caller's host arrays (MATCH_ROW_DTYPE [count, max_rows])."""
+        if isinstance(sample_off, tuple):                   # (win_begin, win_end): windows may overlap
+            b, bp = self._off(sample_off[0])
+            e_, ep = self._off(sample_off[1])
+            n = len(b)
+            cnt = n - rows_first if rows_count is None else int(rows_count)
+            self._check(self._L.aid_identify_exchange_windows_host(self._h, xchg._h, _ptr(pcm), bp, ep, n, _ptr(d_track_map),
+                                                                   int(n_map), int(rows_first), cnt, _ptr(rows), int(max_rows),
+                                                                   _ptr(n_rows)))
+            return
         sample_off, offp = self._off(sample_off)
         n = len(sample_off) - 1
         cnt = n - rows_first if rows_count is None else int(rows_count)
@@ -384,9 +421,10 @@ class Engine:
         return out
 
     def synth_tracks(self, d_pcm, first_track: int, n_tracks: int, samples_per_track: int, seed: int = 42,
-                     stream=None) -> None:
-        self._check(self._L.aid_synth_tracks_dev(self._h, _ptr(d_pcm), int(first_track), int(n_tracks),
-                                                 int(samples_per_track), int(seed), _ptr(stream)))
+                     stream=None, stride: int = 1) -> None:
+        """Track k of the batch is global track first_track + k * stride of the deterministic device corpus."""
+        self._check(self._L.aid_synth_tracks_strided_dev(self._h, _ptr(d_pcm), int(first_track), int(stride), int(n_tracks),
+                                                         int(samples_per_track), int(seed), _ptr(stream)))
 
 
 class Exchange:

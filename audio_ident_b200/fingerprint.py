@@ -268,33 +268,52 @@ def index_tracks_sync(items: Sequence[tuple[bytes, uuid.UUID]]) -> list[bool]:
     return out
 
 
-def query_many_sync(clips: Sequence[bytes]) -> list[list[OlafMatch]]:
-    from .engine import ragged
+_MAX_WINDOW_SAMPLES = (32768 - 1) * 128 + 1024            # AID_QUERY_MAX_FRAMES frames per vote window
 
-    out: list[list[OlafMatch]] = [[] for _ in clips]
-    live = [i for i, c in enumerate(clips) if c]
-    if not live:
+
+def query_windows_sync(clips: Sequence[bytes], windows: Sequence[tuple[int, int, int]]) -> list[list[OlafMatch]]:
+    """One engine call for windows (clip index, first sample, one-past-last sample) over a batch of clips. Windows of one
+    clip may overlap -- the exact lane's three sub-windows of a 5 s clip (exact.py:48-52) -- and every clip crosses PCIe
+    once (aid_query_windows_host). Result i is what ``olaf_query(clip[first:last])`` returns: times relative to the
+    window, rows sorted by match_count descending."""
+    out: list[list[OlafMatch]] = [[] for _ in windows]
+    arrs = [np.frombuffer(c, dtype="<f4") if c else np.zeros(0, "<f4") for c in clips]
+    base = np.zeros(len(arrs) + 1, np.int64)
+    if arrs:
+        base[1:] = np.cumsum([len(a) for a in arrs])
+    begin, end, owner, starts = [], [], [], []
+    for w, (ci, lo, hi) in enumerate(windows):
+        lo = max(0, min(int(lo), len(arrs[ci]))); hi = max(lo, min(int(hi), len(arrs[ci])))
+        if hi <= lo:
+            continue
+        for s0 in range(lo, hi, _MAX_WINDOW_SAMPLES):        # a window longer than the vote-window limit is cut into several
+            begin.append(base[ci] + s0); end.append(base[ci] + min(s0 + _MAX_WINDOW_SAMPLES, hi))
+            owner.append(w); starts.append((s0 - lo) // 128)
+    if not begin:
         return out
     eng = get_engine()
     with _state.lock:
-        windows, owner, starts = [], [], []
-        max_samples = (32768 - 1) * 128 + 1024            # AID_QUERY_MAX_FRAMES per vote window
-        for i in live:
-            arr = np.frombuffer(clips[i], dtype="<f4")
-            for s in range(0, max(len(arr), 1), max_samples):
-                windows.append(arr[s:s + max_samples]); owner.append(i); starts.append(s // 128)
-        pcm, off = ragged(windows)
-        rows, n = eng.query(pcm, off)
-        for w, i in enumerate(owner):
-            for r in rows[w][:n[w]]:
-                name = eng.track_name(int(r["track"]))
-                q0, q1 = int(r["q_first"]) + starts[w], int(r["q_last"]) + starts[w]
-                off_f = int(r["offset"]) - starts[w]
-                out[i].append(OlafMatch(int(r["count"]), q0 * FRAME_SECONDS, q1 * FRAME_SECONDS, name, int(r["track"]),
+        pcm = np.concatenate(arrs).astype(np.float32, copy=False)
+        rows, n = eng.query_windows(pcm, np.asarray(begin, np.int64), np.asarray(end, np.int64))
+        names: dict[int, str] = {}
+        for k, w in enumerate(owner):
+            for r in rows[k][:n[k]]:
+                tr = int(r["track"])
+                name = names.get(tr)
+                if name is None:
+                    name = names[tr] = eng.track_name(tr)
+                q0, q1 = int(r["q_first"]) + starts[k], int(r["q_last"]) + starts[k]
+                off_f = int(r["offset"]) - starts[k]
+                out[w].append(OlafMatch(int(r["count"]), q0 * FRAME_SECONDS, q1 * FRAME_SECONDS, name, tr,
                                         (q0 + off_f) * FRAME_SECONDS, (q1 + off_f) * FRAME_SECONDS))
     for lst in out:
         lst.sort(key=lambda m: m.match_count, reverse=True)   # stable: engine order breaks ties
     return out
+
+
+def query_many_sync(clips: Sequence[bytes]) -> list[list[OlafMatch]]:
+    """Independent result lists for a batch of clips (each one whole window), one GPU pass."""
+    return query_windows_sync(clips, [(i, 0, len(c) // 4) for i, c in enumerate(clips)])
 
 
 def delete_track_sync(track_id: uuid.UUID) -> bool:
@@ -422,6 +441,11 @@ async def olaf_delete_track(track_id: uuid.UUID) -> bool:
 async def index_tracks(items: Sequence[tuple[bytes, uuid.UUID]]) -> list[bool]:
     """Batch form of olaf_index_track: one GPU pass for the whole list."""
     return await _in_thread(index_tracks_sync, list(items))
+
+
+async def query_windows(clips: Sequence[bytes], windows: Sequence[tuple[int, int, int]]) -> list[list[OlafMatch]]:
+    """Batch form for overlapping windows (clip index, first sample, one-past-last sample): see query_windows_sync."""
+    return await _in_thread(query_windows_sync, list(clips), list(windows))
 
 
 async def query_many(clips: Sequence[bytes]) -> list[list[OlafMatch]]:

@@ -98,10 +98,14 @@ def identify_stream(identifier, pcm, n_samples: int, window_s: float = 10.0, hop
         import torch
         src = pcm if hasattr(pcm, "data_ptr") else None
         assert src is not None, "device=True expects a torch CUDA tensor"
-        idx = torch.from_numpy(starts).to(src.device)[:, None] + torch.arange(w, device=src.device)[None, :]
-        buf = src[idx].contiguous()
-        off = np.arange(len(starts) + 1, dtype=np.int64) * w
-        merged, n = identifier.query(buf.data_ptr(), off, device=True)
+        if getattr(identifier, "_xchg", None) is not None and len(starts) <= identifier._xchg.max_queries:
+            # the windows are fingerprinted where they lie in the recording (overlapping ranges, no gather, no copy)
+            merged, n = identifier.query(src.data_ptr(), (starts, starts + w), device=True)
+        else:
+            idx = torch.from_numpy(starts).to(src.device)[:, None] + torch.arange(w, device=src.device)[None, :]
+            buf = src[idx].contiguous()
+            off = np.arange(len(starts) + 1, dtype=np.int64) * w
+            merged, n = identifier.query(buf.data_ptr(), off, device=True)
         m = merged.cpu().numpy(); nn = n.cpu().numpy()
     else:
         pcm = np.ascontiguousarray(pcm, np.float32)

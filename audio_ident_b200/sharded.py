@@ -173,7 +173,7 @@ class ShardedIdentifier:
         and rows exchanged through the ranks' windows over NVLink, merge on the device. No NCCL call, no host
         synchronisation; the only torch work is shaping the result."""
         import torch
-        n = len(sample_off) - 1
+        n = len(sample_off[0]) if isinstance(sample_off, tuple) else len(sample_off) - 1
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=self.device)
         self._stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -266,8 +266,12 @@ class ShardedIdentifier:
         from ._lib import MATCH_ROW_DTYPE
         if self._xchg is None:
             raise RuntimeError("enable_peer_exchange() first")
-        sample_off = np.ascontiguousarray(sample_off, np.int64)
-        n = len(sample_off) - 1
+        if isinstance(sample_off, tuple):                    # (win_begin, win_end): overlapping windows, one copy of the span
+            sample_off = (np.ascontiguousarray(sample_off[0], np.int64), np.ascontiguousarray(sample_off[1], np.int64))
+            n = len(sample_off[0])
+        else:
+            sample_off = np.ascontiguousarray(sample_off, np.int64)
+            n = len(sample_off) - 1
         cnt = n - rows_first if rows_count is None else int(rows_count)
         if self._map_dev is None:
             self._map_dev = torch.tensor(self.to_global if self.to_global else [0], dtype=torch.int32, device=self.device)
@@ -284,6 +288,13 @@ class ShardedIdentifier:
         fingerprints windows [r*n/P, (r+1)*n/P)) so that no stage is replicated. With the peer exchange enabled the
         step is asynchronous; check=True (default) waits for it and raises if a rank failed to deliver -- a failed
         exchange must not read as "no match". Callers that pipeline steps pass check=False and call check() later."""
+        if isinstance(sample_off, tuple):                    # (win_begin, win_end) over device PCM: the fused path only
+            if not (device and self._xchg is not None and len(sample_off[0]) <= self._xchg.max_queries):
+                raise ValueError("overlapping windows need device PCM and the peer exchange (enable_peer_exchange)")
+            out = self._query_fused(pcm, (np.ascontiguousarray(sample_off[0], np.int64), np.ascontiguousarray(sample_off[1], np.int64)))
+            if check:
+                self._xchg.check()
+            return out
         sample_off = np.ascontiguousarray(sample_off, np.int64)
         n = len(sample_off) - 1
         if device and self.device is not None and split_fingerprint and n >= self.world and hasattr(self.backend, "match_dev"):

@@ -45,6 +45,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries the JSON line and nothing else: NCCL writes its banner (and, with NCCL_DEBUG set, its whole log) to fd 1
+# from C, so fd 1 is pointed at stderr for the life of the process and the line goes out through a saved descriptor.
+# NCCL's log therefore stays visible (on stderr) at whatever level the caller asked for.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -228,10 +250,7 @@ def main():
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its log (and, at any debug level, its version banner) to stdout, where the JSON line goes:
-        # keep the level the driver asked for, send the log to a file, echo the communicator lines to stderr at exit
-        nccl_log = os.path.join(tempfile.gettempdir(), f"aid_nccl_{os.getpid()}.log")
-        os.environ.setdefault("NCCL_DEBUG_FILE", nccl_log)
+        claim_stdout()                               # NCCL's banner / log: stderr, at the level the caller asked for
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -445,7 +464,7 @@ def main():
                   "note": "every differing track was re-run stage by stage (oracle/parity.py): all differences are float "
                           "near-tie peaks" if not unexplained else "UNEXPLAINED DIFFERENCES"}
         if unexplained or len(differing) > max(16, nc // 32):
-            print(json.dumps({"error": "parity_sample failed", "parity_sample": parity}), flush=True)
+            emit({"error": "parity_sample failed", "parity_sample": parity})
             raise SystemExit(3)
 
     # ---- second half of the metric: identification (and configs[4], long form) on the same ranks
@@ -484,17 +503,9 @@ def main():
             "per_gpu_value": value / world,
             "identify": identify, "longform": longform,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
-        try:                                    # what the driver looks for in NCCL's log, on stderr instead of stdout
-            path = os.environ.get("NCCL_DEBUG_FILE", "")
-            if rank == 0 and path and os.path.exists(path):
-                for ln in open(path, errors="replace"):
-                    if "nranks" in ln or "Init COMPLETE" in ln or "NVLS" in ln and "comm" in ln:
-                        sys.stderr.write(ln)
-        except Exception:
-            pass
     eng.close()
 
 

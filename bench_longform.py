@@ -50,11 +50,7 @@ def longform_block(eng, rank, world, dev, seed=42, hours=3.0, tracks=20000, wind
     off_full = np.arange(513, dtype=np.int64) * samples
     for c0 in range(0, len(mine), 512):
         ids = mine[c0:c0 + 512]
-        if world == 1:
-            eng.synth_tracks(buf.data_ptr(), int(ids[0]), len(ids), samples, seed)
-        else:
-            for j, g in enumerate(ids):
-                eng.synth_tracks(buf.data_ptr() + j * samples * 4, int(g), 1, samples, seed)
+        eng.synth_tracks(buf.data_ptr(), int(ids[0]), len(ids), samples, seed, stride=world)
         assert sh.add(buf.data_ptr(), off_full[:len(ids) + 1], [int(g) for g in ids], device=True).all()
     eng.index_commit()
     del buf
@@ -129,7 +125,7 @@ def longform_block(eng, rank, world, dev, seed=42, hours=3.0, tracks=20000, wind
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": t_id * 1e3, "scaling": "strong",
         "workload": f"{rec_hours:.2f} h recording ({n_items} x 30 s tracks + 6 s gaps), {len(starts)} vote windows of "
                     f"{window_s:g} s every {hop_s:g} s, index of {tracks} tracks sharded over {world} rank(s)",
-        "timed_region": "recording resident in HBM -> window gather -> fingerprint (windows split over ranks) -> peer-memory "
+        "timed_region": "recording resident in HBM -> overlapping windows fingerprinted in place (split over ranks) -> peer-memory "
                         "exchange -> merged rows -> host segment stitching (wall clock, max over ranks)",
         "segments_found": len(segs), "playlist_items": int(n_items), "segments_in_order_and_correct": int(correct),
         "max_start_error_s": max(start_err) if start_err else None, "rows_digest": digest,

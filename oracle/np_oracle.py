@@ -79,6 +79,8 @@ def resample3(x: np.ndarray) -> np.ndarray:
     the engine uses (what csrc/resample.cu must reproduce); scipy.signal.resample_poly(x, 1, 3) is the same up to the
     rounding of the taps (tests/test_oracle.py)."""
     x = np.asarray(x, np.float64)
+    if len(x) == 0:
+        return np.zeros(0, np.float64)
     h = resample_taps().astype(np.float32).astype(np.float64)
     full = np.convolve(x, h)                      # full[i] = sum_k h[k] x[i - k]; y[j] = full[3 j + 30]
     n_out = (len(x) + 2) // 3

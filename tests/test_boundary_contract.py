@@ -140,3 +140,17 @@ def test_missing_engine_raises_olaf_error(monkeypatch):
         asyncio.run(fp.olaf_index_track(bytes(64000), uuid.uuid4()))
     with pytest.raises(fp.OlafError):
         asyncio.run(fp.olaf_delete_track(uuid.uuid4()))
+
+
+def test_window_ranges_equal_the_byte_slices():
+    """exact_lane.plan_window_ranges (offsets into the clip, for the one-upload window query) describes exactly the
+    byte strings plan_windows / the reference's _extract_pcm_window cut out (exact.py:374-399)."""
+    from audio_ident_b200 import exact_lane as xl
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15999, 16000, 23999, 24000, 24001, 56000, 67999, 68000, 79999, 80000, 80001, 200000):
+        pcm = rng.standard_normal(n).astype("<f4").tobytes()
+        short, wins = xl.plan_windows(pcm)
+        short2, ranges = xl.plan_window_ranges(pcm)
+        assert short == short2 and len(wins) == len(ranges)
+        for w, r in zip(wins, ranges):
+            assert (pcm[r[0] * 4:r[1] * 4] if r is not None else b"") == w

@@ -38,6 +38,14 @@ def test_index_query_delete_roundtrip(index_dir):
     assert res[0] and res[0][0].track_uuid == ids[3] and res[0][0].aligned_hashes >= 8 and 0 < res[0][0].confidence <= 1.0
     assert res[1] == []
     assert res[2] and res[2][0].track_uuid == ids[1] and abs(res[2][0].offset_seconds) < 0.2
+    # the one-upload window form (offsets into the clip) equals the three separate window queries of the reference's loop
+    res_bytes = exact_lane.score_clips([clip.tobytes(), b"", tracks[1][:16000 * 8].tobytes()], max_results=3,
+                                       query_many=fp.query_many_sync)
+    assert res == res_bytes
+    wins = [(0, 0, 56000), (0, 12000, 68000), (0, 24000, 80000)]
+    by_offsets = fp.query_windows_sync([clip.tobytes()], wins)
+    by_copies = fp.query_many_sync([clip[a:b].tobytes() for _, a, b in wins])
+    assert by_offsets == by_copies and all(by_offsets)
     # delete
     assert asyncio.run(fp.olaf_delete_track(ids[3])) is True
     assert asyncio.run(fp.olaf_delete_track(ids[3])) is False
