@@ -1,7 +1,12 @@
-"""The real multi-process exchange: two processes on one GPU, each with its own engine and half of the tracks, swap the
+"""The real multi-process exchange: two processes, one per GPU, each with its own engine and half of the tracks, swap the
 64-byte handles of aid_exchange_handle through a pipe, map each other's receive window with aid_exchange_connect
-(cudaIpcOpenMemHandle) and run the fused identification step (aid_identify_exchange_dev and _host). Both must end up
-with the rows of one unsharded index. Everything the torchrun path does, minus NCCL."""
+(cudaIpcOpenMemHandle over NVLink) and run the fused identification step (aid_identify_exchange_dev and _host). Both must
+end up with the rows of one unsharded index. Everything the torchrun path does, minus NCCL.
+
+Needs TWO GPUs (skipped otherwise): the ranks' kernels wait for each other's flags on the device, and processes that
+time-slice ONE GPU are not guaranteed to run at the same time (B200_PROFILING.md warns of Xid 109 for exactly that).
+Run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_ipc_exchange.py -m gpu`; the log of that run is committed
+under profiles/. (Ranks that share one process and one GPU -- tests/test_gpu_sharded.py -- use connect_local.)"""
 import multiprocessing as mp
 import os
 import sys
@@ -32,14 +37,14 @@ def _rank_main(rank, world, conn, out_q):
     from audio_ident_b200.engine import Engine, ragged
     try:
         tracks, wins = _corpus()
-        eng = Engine(0)
-        sh = sharded.ShardedIdentifier(eng, rank, world, device=torch.device("cuda", 0))
+        torch.cuda.set_device(rank)
+        eng = Engine(rank)                                  # one process per GPU
+        sh = sharded.ShardedIdentifier(eng, rank, world, device=torch.device("cuda", rank))
         mine = sh.my_tracks(len(tracks))
         p, o = ragged([tracks[g] for g in mine])
         assert sh.add(p, o, mine).all()
         eng.index_commit()
         sh.enable_peer_exchange(64, connect=False)
-        sh._xchg.set_timeout_ms(60000)                    # two contexts time-slice one GPU: be patient
         conn.send(sh._xchg.handle())                      # 64-byte cudaIpcMemHandle_t to the peer ...
         peer = conn.recv()                                # ... and the peer's back
         handles = [None, None]
@@ -64,8 +69,11 @@ def _rank_main(rank, world, conn, out_q):
         out_q.put((rank, "error", traceback.format_exc(), None))
 
 
-def test_two_processes_one_gpu_cuda_ipc(engine):
-    from audio_ident_b200 import sharded
+def test_two_processes_two_gpus_cuda_ipc(engine):
+    import ctypes
+    from audio_ident_b200 import _lib, sharded
+    if _lib.load().aid_device_count() < 2:
+        pytest.skip("needs two GPUs: the ranks' kernels wait on each other and must not time-slice one device")
     from audio_ident_b200.engine import ragged
     tracks, wins = _corpus()
     engine.index_clear()
