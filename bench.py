@@ -326,7 +326,7 @@ def main():
     # DRAM bytes per launch from the committed ncu capture (profiles/traffic_r01.json), scaled to this run's average
     # launch size; None if the capture is missing
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
     except Exception:
         cap = None
     for name, b in (("stft", stft_bytes), ("peaks", peaks_bytes)):
@@ -345,7 +345,7 @@ def main():
     roofline = {k: kern["stft"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = "k_stft"
     roofline["peak_source"] = peak_src
-    roofline["traffic_source"] = "profiles/traffic_r01.json (ncu --set full), scaled to this run's launch size"
+    roofline["traffic_source"] = "profiles/traffic_r02.json (ncu --set full), scaled to this run's launch size"
 
     # ---- end to end through the host-buffer C ABI call
     e2e = None
