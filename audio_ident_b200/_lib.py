@@ -71,7 +71,6 @@ def load() -> C.CDLL:
         "aid_index_commit": (C.c_int, [vp]),
         "aid_index_clear": (C.c_int, [vp]),
         "aid_index_set_grouping": (C.c_int, [vp, C.c_int]),
-        "aid_index_set_group_matcher": (C.c_int, [vp, C.c_int]),
         "aid_index_stats": (C.c_int, [vp, i64p]),
         "aid_index_track_name": (C.c_int, [vp, C.c_uint32, C.c_char_p, C.c_int]),
         "aid_index_save": (C.c_int, [vp, C.c_char_p]),
@@ -137,7 +136,7 @@ EXPORTED = [  # every symbol include/audio_ident_b200.h declares (tests/test_abi
     "aid_engine_destroy", "aid_last_error", "aid_launch_count", "aid_engine_sync",
     "aid_engine_set_max_batch_frames", "aid_engine_set_stage_timing", "aid_engine_stage_times", "aid_fingerprint_host", "aid_fingerprint_dev", "aid_stft_host",
     "aid_peaks_host", "aid_hashes_host", "aid_num_frames", "aid_index_add_host", "aid_index_add_host_fp", "aid_index_add_dev",
-    "aid_index_add_hashes", "aid_index_delete", "aid_index_commit", "aid_index_clear", "aid_index_set_grouping", "aid_index_set_group_matcher", "aid_index_stats",
+    "aid_index_add_hashes", "aid_index_delete", "aid_index_commit", "aid_index_clear", "aid_index_set_grouping", "aid_index_stats",
     "aid_index_track_name", "aid_index_save", "aid_index_load", "aid_query_host", "aid_query_dev", "aid_query_windows_host",
     "aid_query_hashes", "aid_match_dev", "aid_exchange_create", "aid_exchange_destroy", "aid_exchange_handle",
     "aid_exchange_connect", "aid_exchange_connect_local", "aid_exchange_set_timeout_ms", "aid_exchange_status",

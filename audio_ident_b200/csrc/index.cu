@@ -160,7 +160,6 @@ void aid_index_free(aid_engine*, Index* ix) {
     for (Segment* s : ix->segs) { s->release(); delete s; }
     for (SegGroup* g : ix->groups) { if (g) { g->release(); delete g; } }
     ix->cursor.release(); ix->scan_tmp.release(); ix->d_jobs.release(); ix->d_segdesc.release(); ix->group_start.release();
-    ix->d_plaindesc.release(); ix->d_groupdesc.release(); ix->d_unitdesc.release();
     ix->cand.release(); ix->cand_n.release(); ix->rows.release(); ix->rows_n.release(); ix->vote_stats.release();
     delete ix;
 }
@@ -368,32 +367,6 @@ int aid_index_commit_on(aid_engine* e, cudaStream_t st) {
         AID_CUDA(e, ix->d_segdesc.ensure(std::max<size_t>(d.size(), 1) * sizeof(aid_seg_desc)));
         AID_CUDA(e, cudaStreamSynchronize(st));
         if (!d.empty()) AID_CUDA(e, cudaMemcpy(ix->d_segdesc.p, d.data(), d.size() * sizeof(aid_seg_desc), cudaMemcpyHostToDevice));
-        // match units: plain segments keep one CTA per (window, segment); a group is ONE unit (k_match_group)
-        std::vector<aid_seg_desc> plain;
-        std::vector<aid_group_desc> gd;
-        std::vector<aid_unit_desc> ud;
-        for (size_t i = 0; i < d.size(); i++)
-            if (!ix->group_matcher || ix->segs[i]->group < 0) { plain.push_back(d[i]); ud.push_back({d[i].first_track}); }
-        if (ix->group_matcher)
-            for (SegGroup* g : ix->groups) {
-                if (!g || !g->dir.p || g->n_segs == 0 || g->n_segs == 0xffffffffu) continue;
-                aid_group_desc x{};
-                x.dir = g->dir.as<uint32_t>(); x.postings = g->postings.as<uint32_t>();
-                x.first_track = ix->segs[g->first_seg]->first_track; x.n_segs = g->n_segs;
-                for (uint32_t j = 0; j < g->n_segs; j++) {
-                    const Segment* sg = ix->segs[g->first_seg + j];
-                    x.tomb[j] = sg->tomb.as<uint32_t>();
-                    if (sg->n_deleted) x.deleted_mask |= 1u << j;
-                }
-                gd.push_back(x); ud.push_back({x.first_track});
-            }
-        ix->n_plain = (int)plain.size(); ix->n_group_units = (int)gd.size();
-        AID_CUDA(e, ix->d_plaindesc.ensure(std::max<size_t>(plain.size(), 1) * sizeof(aid_seg_desc)));
-        AID_CUDA(e, ix->d_groupdesc.ensure(std::max<size_t>(gd.size(), 1) * sizeof(aid_group_desc)));
-        AID_CUDA(e, ix->d_unitdesc.ensure(std::max<size_t>(ud.size(), 1) * sizeof(aid_unit_desc)));
-        if (!plain.empty()) AID_CUDA(e, cudaMemcpy(ix->d_plaindesc.p, plain.data(), plain.size() * sizeof(aid_seg_desc), cudaMemcpyHostToDevice));
-        if (!gd.empty()) AID_CUDA(e, cudaMemcpy(ix->d_groupdesc.p, gd.data(), gd.size() * sizeof(aid_group_desc), cudaMemcpyHostToDevice));
-        if (!ud.empty()) AID_CUDA(e, cudaMemcpy(ix->d_unitdesc.p, ud.data(), ud.size() * sizeof(aid_unit_desc), cudaMemcpyHostToDevice));
         ix->segdesc_dirty = false;
     }
     return AID_OK;
@@ -537,11 +510,10 @@ extern "C" int aid_index_clear(aid_engine* e) {
     if (!e) return AID_E_ARG;
     AID_CUDA(e, cudaSetDevice(e->device));
     AID_CUDA(e, cudaDeviceSynchronize());
-    const bool grouping = e->index->grouping, group_matcher = e->index->group_matcher;
+    const bool grouping = e->index->grouping;
     aid_index_free(e, e->index);
     e->index = aid_index_new();
     e->index->grouping = grouping;
-    e->index->group_matcher = group_matcher;
     return AID_OK;
 }
 
@@ -558,15 +530,6 @@ extern "C" int aid_index_set_grouping(aid_engine* e, int on) {
         for (Segment* s : ix->segs) if (s->group >= 0) { s->group = -1; s->sub = 0; s->dirty = true; }
     }
     ix->segdesc_dirty = true;
-    return AID_OK;
-}
-
-extern "C" int aid_index_set_group_matcher(aid_engine* e, int on) {
-    if (!e) return AID_E_ARG;
-    AID_CUDA(e, cudaSetDevice(e->device));
-    AID_CUDA(e, cudaDeviceSynchronize());
-    e->index->group_matcher = on != 0;
-    e->index->segdesc_dirty = true;
     return AID_OK;
 }
 

@@ -49,22 +49,6 @@ struct aid_seg_desc {
     uint32_t n_deleted;            // 0: the matcher skips the tombstone lookup
 };
 
-// what the group matcher (k_match_group) needs of a whole segment group: one CTA per (window, group) reads ONE directory
-// entry per query hash and walks the members' adjacent posting runs as one run
-struct aid_group_desc {
-    const uint32_t* dir;           // u32[2^24][8]
-    const uint32_t* postings;
-    const uint32_t* tomb[kGroupSegs];
-    uint32_t first_track;          // engine-wide number of member 0's local track 0; member j starts AID_SEG_TRACKS * j later
-    uint32_t n_segs;
-    uint32_t deleted_mask;         // bit j: member j has tombstones
-    uint32_t pad;
-};
-
-// a match unit = what one CTA of the vote covers: a plain segment (k_match) or a group (k_match_group); k_rank turns a
-// candidate (unit, member, local track) into an engine-wide track number with this
-struct aid_unit_desc { uint32_t first_track; };
-
 struct Index {
     std::vector<TrackInfo> tracks;                       // by engine-wide track number
     std::unordered_map<std::string, uint32_t> by_name;   // live tracks only
@@ -74,10 +58,6 @@ struct Index {
     int64_t live_tracks = 0, n_postings = 0;
     DevBuf cursor, scan_tmp, d_jobs, d_segdesc, group_start;
     bool segdesc_dirty = true;
-    // match units (rebuilt with d_segdesc): the plain segments first (d_plaindesc), then the groups (d_groupdesc)
-    bool group_matcher = true;                           // aid_index_set_group_matcher: off = one CTA per (window, segment) everywhere
-    DevBuf d_plaindesc, d_groupdesc, d_unitdesc;
-    int n_plain = 0, n_group_units = 0;
     // matcher workspace
     DevBuf cand, cand_n, rows, rows_n;
     DevBuf vote_stats;                                   // u64[1024][2]: hashes probed, postings touched (aid_match_stats)

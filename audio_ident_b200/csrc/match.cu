@@ -32,17 +32,17 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kSketch = 2048;
-constexpr int kTable = 256;
-constexpr int kTableMaxLoad = 192;
-constexpr int kQChunk = 512;
+constexpr int kTable = 128;
+constexpr int kTableMaxLoad = 96;
+constexpr int kQChunk = 256;               // query hashes staged at a time (a 3.5 s window has ~110)
 constexpr int kVotesPerRound = 2048;       // = kSketch: ~1 vote per counter keeps chance counts >= AID_MIN_VOTES at ~1 per round; a (window, segment) CTA
                                             // sees ~1,000 votes, so the usual CTA needs one round, not two (each round reads every posting twice)
 constexpr int kBest = 64;                 // >= AID_MAX_ROWS, power of two
-constexpr int kSortN = 512;               // kTable + kBest <= kSortN
+constexpr int kSortN = 256;               // kTable + kBest <= kSortN
 constexpr uint32_t kEmpty = 0xffffffffu;
 constexpr uint64_t kPad = ~0ull;
 
-struct CandEntry { uint32_t inv_count; uint32_t key; uint32_t tq; uint32_t sub; };   // tq = q_first | q_last << 16; sub = member of a group unit (0 for a plain segment)
+struct CandEntry { uint32_t inv_count; uint32_t key; uint32_t tq; };   // tq = q_first | q_last << 16
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void bitonic_sort_n(uint64_t* key, uint32_t* val, int
 
 constexpr int kOwnerCap = kSortN * 6;       // u16 entries that fit the sort buffers (skey + sval), which are idle during the vote loops
 struct MatchSmem {
-    alignas(16) uint32_t sketch[kSketch];
+    alignas(16) uint32_t sketch[kSketch / 2];      // 16-bit counters, two per word: a round never holds more than 2048 votes
     alignas(16) uint32_t tkey[kTable], tcnt[kTable], tmin[kTable], tmax[kTable];
     uint32_t qbeg[kQChunk], qadd[kQChunk], qstart[kQChunk + 1];
     alignas(16) uint64_t skey[kSortN];     // skey + sval double as the vote -> hash map `owner` (u16[kOwnerCap])
@@ -99,20 +99,21 @@ struct MatchSmem {
     uint32_t total, used, overflow, nbest, hit, maybe;
 };
 
-__global__ void __launch_bounds__(kThreads)
+// 17 KB of shared memory and <= 40 registers: 12 CTAs (48 warps) per SM. The kernel waits on chains of dependent random
+// loads (hash -> directory entry -> posting run), so resident CTAs are what hides them.
+__global__ void __launch_bounds__(kThreads, 16)
 k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, const uint32_t* __restrict__ hash_off,
         const uint32_t* __restrict__ hash_len, const int32_t* __restrict__ q_status,
-        const aid_seg_desc* __restrict__ segs, int n_seg, int n_units,
+        const aid_seg_desc* __restrict__ segs, int n_seg,
         CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n,
         const uint32_t* __restrict__ abort_flag, unsigned long long* __restrict__ vote_stats) {
     __shared__ MatchSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = blockIdx.x / n_seg, sg = blockIdx.x % n_seg;
-    const int64_t out_slot = (int64_t)q * n_units + sg;          // plain segments are the first n_seg match units
     // sharded identification: the wait for the peers' query fingerprints gave up (k_wait_hashes) -- the hash window is
     // only partly written, so nothing is probed; k_rank still publishes (empty) blocks and the merge reports -1 rows
     if (abort_flag && *abort_flag) {
-        if (tid == 0) cand_n[out_slot] = 0;
+        if (tid == 0) cand_n[blockIdx.x] = 0;
         return;
     }
     const aid_seg_desc seg = segs[sg];
@@ -205,7 +206,7 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
         atomicAdd(vote_stats + 2 * (blockIdx.x & 1023u) + 1, (unsigned long long)total);
     }
     if (total < AID_MIN_VOTES) {
-        if (tid == 0) cand_n[out_slot] = 0;
+        if (tid == 0) cand_n[blockIdx.x] = 0;
         return;
     }
     uint32_t R = (total + kVotesPerRound - 1) / kVotesPerRound;
@@ -216,7 +217,7 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     for (;;) {                                        // restarted with a finer partition if the exact table fills
         if (tid == 0) { sm.nbest = 0; sm.overflow = 0; }
         for (uint32_t r = 0; r < R; r++) {
-            if (!direct) for (int i = tid; i < kSketch / 4; i += kThreads) reinterpret_cast<uint4*>(sm.sketch)[i] = make_uint4(0, 0, 0, 0);
+            if (!direct) for (int i = tid; i < kSketch / 8; i += kThreads) reinterpret_cast<uint4*>(sm.sketch)[i] = make_uint4(0, 0, 0, 0);
             for (int i = tid; i < kTable / 4; i += kThreads) {
                 reinterpret_cast<uint4*>(sm.tkey)[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
                 reinterpret_cast<uint4*>(sm.tcnt)[i] = make_uint4(0, 0, 0, 0);
@@ -242,32 +243,52 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
                             for (uint32_t v = sm.qstart[i], ve = sm.qstart[i + 1]; v < ve; v++) owner[v] = (uint16_t)i;
                         __syncthreads();
                     }
-                    for (uint32_t v = tid; v < nv; v += kThreads) {
-                        uint32_t lo = 0;
-                        if (mapped) lo = owner[v];
-                        else { uint32_t hi = nc; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; } }
-                        const uint32_t post = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
-                        const uint32_t local = post >> AID_POST_T_BITS;
-                        if (any_deleted && (seg.tomb[local >> 5] & (1u << (local & 31)))) continue;
-                        const uint32_t key = post + sm.qadd[lo];
-                        const uint32_t m = mix32(key);
-                        if (R > 1 && (m >> 12) % R != r) continue;
-                        const uint32_t idx = m & (kSketch - 1);
-                        if (pass == 0) { if (atomicAdd(&sm.sketch[idx], 1u) + 1 == AID_MIN_VOTES) sm.maybe = 1; continue; }
-                        if (!direct && sm.sketch[idx] < AID_MIN_VOTES) continue;
-                        const uint32_t tq = AID_QUERY_MAX_FRAMES - sm.qadd[lo];
-                        uint32_t slot = (m >> 20) & (kTable - 1);
-                        for (int probe = 0; probe < kTable; probe++) {
-                            const uint32_t old = atomicCAS(&sm.tkey[slot], kEmpty, key);
-                            if (old == kEmpty) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
-                            if (old == kEmpty || old == key) {
-                                if (atomicAdd(&sm.tcnt[slot], 1u) + 1 == AID_MIN_VOTES) sm.hit = 1;   // a row is born
-                                atomicMin(&sm.tmin[slot], tq);
-                                atomicMax(&sm.tmax[slot], tq);
-                                break;
+                    // Four votes per thread and trip, their posting loads issued before any of them is counted: the
+                    // kernel waits on these random loads (ncu: 6.8 long-scoreboard stalls per issued instruction at 39 %
+                    // issue utilisation), so memory-level parallelism is what it needs, not fewer instructions.
+                    constexpr int kUnroll = 4;
+                    for (uint32_t v0 = tid; v0 < nv; v0 += kUnroll * kThreads) {
+                        uint32_t los[kUnroll], posts[kUnroll];
+#pragma unroll
+                        for (int j = 0; j < kUnroll; j++) {
+                            const uint32_t v = v0 + j * kThreads;
+                            uint32_t lo = 0;
+                            if (v < nv) {
+                                if (mapped) lo = owner[v];
+                                else { uint32_t hi = nc; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.qstart[mid] <= v) lo = mid; else hi = mid; } }
+                                posts[j] = postings[sm.qbeg[lo] + (v - sm.qstart[lo])];
                             }
-                            slot = (slot + 1) & (kTable - 1);
-                            if (probe == kTable - 1) sm.overflow = 1;
+                            los[j] = lo;
+                        }
+#pragma unroll
+                        for (int j = 0; j < kUnroll; j++) {
+                            if (v0 + j * kThreads >= nv) continue;
+                            const uint32_t lo = los[j], post = posts[j];
+                            const uint32_t local = post >> AID_POST_T_BITS;
+                            if (any_deleted && (seg.tomb[local >> 5] & (1u << (local & 31)))) continue;
+                            const uint32_t key = post + sm.qadd[lo];
+                            const uint32_t m = mix32(key);
+                            if (R > 1 && (m >> 12) % R != r) continue;
+                            const uint32_t idx = m & (kSketch - 1), sh = 16 * (idx & 1);
+                            if (pass == 0) {
+                                if (((atomicAdd(&sm.sketch[idx >> 1], 1u << sh) >> sh) & 0xffffu) + 1 == AID_MIN_VOTES) sm.maybe = 1;
+                                continue;
+                            }
+                            if (!direct && ((sm.sketch[idx >> 1] >> sh) & 0xffffu) < AID_MIN_VOTES) continue;
+                            const uint32_t tq = AID_QUERY_MAX_FRAMES - sm.qadd[lo];
+                            uint32_t slot = (m >> 20) & (kTable - 1);
+                            for (int probe = 0; probe < kTable; probe++) {
+                                const uint32_t old = atomicCAS(&sm.tkey[slot], kEmpty, key);
+                                if (old == kEmpty) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
+                                if (old == kEmpty || old == key) {
+                                    if (atomicAdd(&sm.tcnt[slot], 1u) + 1 == AID_MIN_VOTES) sm.hit = 1;   // a row is born
+                                    atomicMin(&sm.tmin[slot], tq);
+                                    atomicMax(&sm.tmax[slot], tq);
+                                    break;
+                                }
+                                slot = (slot + 1) & (kTable - 1);
+                                if (probe == kTable - 1) sm.overflow = 1;
+                            }
                         }
                     }
                     __syncthreads();
@@ -304,227 +325,23 @@ k_match(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, c
     }
 
     const uint32_t n = min(sm.nbest, (uint32_t)AID_MAX_ROWS);
-    CandEntry* out = cand + out_slot * AID_MAX_ROWS;
+    CandEntry* out = cand + (int64_t)blockIdx.x * AID_MAX_ROWS;
     if (tid < (int)n) {
         CandEntry c;
         c.inv_count = (uint32_t)(sm.bkey[tid] >> 32);
         c.key = (uint32_t)sm.bkey[tid];
         c.tq = sm.bval[tid];
-        c.sub = 0;
         out[tid] = c;
     }
-    if (tid == 0) cand_n[out_slot] = n;
-}
-
-// ---- k_match_group: one CTA per (query window, segment GROUP) -------------------------------------------------------
-// A group's directory entry of hash h holds the start of ONE contiguous posting run ordered by (member segment, local
-// track, t) and the eight member counts. Where k_match spends one CTA per member -- eight CTAs that each stage the same
-// ~100 query hashes, zero their own sketch and tables and walk ~100 short runs of ~8 postings -- this kernel reads the
-// entry once per hash and a WARP walks the whole run (~60 postings: two coalesced 128 B requests) with the member of a
-// posting found from the cumulative counts in registers. The vote key becomes (member, local track, offset): 35 bits,
-// so keys are 64-bit in the exact table; the sketch has 8192 16-bit counters (a round takes up to 8192 votes, and a
-// counter cannot wrap because a round never holds more than 65535 votes). Everything else -- sketch filter, exact
-// table, rounds over a hash partition of the keys, restart with a finer partition, top-50 by bitonic network -- is
-// k_match's scheme; the rows are bit-identical (tests/test_gpu_index_match.py).
-constexpr int kGThreads = 256;
-constexpr int kGSketch = 8192;              // 16-bit counters, two per word
-constexpr int kGVotesPerRound = 8192;
-constexpr int kGChunk = 512;
-constexpr unsigned long long kEmpty64 = ~0ull;
-
-struct GroupSmem {
-    alignas(16) uint32_t sketch[kGSketch / 2];
-    alignas(16) unsigned long long tkey[kTable];
-    alignas(16) uint32_t tcnt[kTable], tmin[kTable], tmax[kTable];
-    uint32_t qbeg[kGChunk], qadd[kGChunk];
-    alignas(16) uint4 qcnt[kGChunk];          // the eight 16-bit member counts of the hash's run
-    alignas(16) uint64_t skey[kSortN];
-    uint32_t sval[kSortN];
-    uint64_t bkey[kBest];
-    uint32_t bval[kBest];
-    const uint32_t* tomb[kGroupSegs];
-    uint32_t wsum[kGThreads / 32];
-    uint32_t next, total, used, overflow, nbest, hit, maybe;
-};
-
-__global__ void __launch_bounds__(kGThreads)
-k_match_group(const uint32_t* __restrict__ q_hash, const uint32_t* __restrict__ q_t, const uint32_t* __restrict__ hash_off,
-              const uint32_t* __restrict__ hash_len, const int32_t* __restrict__ q_status,
-              const aid_group_desc* __restrict__ groups, int n_groups, int n_plain, int n_units,
-              CandEntry* __restrict__ cand, uint32_t* __restrict__ cand_n,
-              const uint32_t* __restrict__ abort_flag, unsigned long long* __restrict__ vote_stats) {
-    __shared__ GroupSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = blockIdx.x / n_groups, gi = blockIdx.x % n_groups;
-    const int64_t out_slot = (int64_t)q * n_units + n_plain + gi;
-    if (abort_flag && *abort_flag) {
-        if (tid == 0) cand_n[out_slot] = 0;
-        return;
-    }
-    const aid_group_desc& grp = groups[gi];
-    const uint32_t* __restrict__ dir = grp.dir;
-    const uint32_t* __restrict__ postings = grp.postings;
-    const uint32_t deleted_mask = grp.deleted_mask;
-    if (tid < kGroupSegs) sm.tomb[tid] = grp.tomb[tid];
-    const uint32_t h0 = hash_off[q];
-    const uint32_t nh = (q_status && q_status[q] != 0) ? 0u : (hash_len ? hash_len[q] : hash_off[q + 1] - h0);
-
-    // stage hashes [c0, c0 + nc): run start, the eight counts, time bias; returns the chunk's votes (same in every thread)
-    auto stage = [&](uint32_t c0, uint32_t nc) -> uint32_t {
-        uint32_t mine = 0;
-        for (uint32_t i = tid; i < nc; i += kGThreads) {
-            const uint32_t h = q_hash[h0 + c0 + i];
-            const uint4 a = *reinterpret_cast<const uint4*>(dir + (size_t)h * 8);
-            const uint32_t c67 = dir[(size_t)h * 8 + 4];
-            sm.qbeg[i] = a.x;
-            sm.qcnt[i] = make_uint4(a.y, a.z, a.w, c67);
-            sm.qadd[i] = AID_QUERY_MAX_FRAMES - q_t[h0 + c0 + i];
-            mine += (a.y & 0xffffu) + (a.y >> 16) + (a.z & 0xffffu) + (a.z >> 16) + (a.w & 0xffffu) + (a.w >> 16) +
-                    (c67 & 0xffffu) + (c67 >> 16);
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(AID_FULL_MASK, mine, d);
-        __syncthreads();                                   // wsum may still be read by the previous call
-        if (lane == 0) sm.wsum[warp] = mine;
-        __syncthreads();
-        uint32_t t = 0;
-#pragma unroll
-        for (int w = 0; w < kGThreads / 32; w++) t += sm.wsum[w];
-        return t;
-    };
-
-    const bool single = nh <= (uint32_t)kGChunk;
-    uint32_t total;
-    if (single) {
-        total = stage(0, nh);
-    } else {
-        total = 0;
-        for (uint32_t c0 = 0; c0 < nh; c0 += kGChunk) total += stage(c0, min((uint32_t)kGChunk, nh - c0));
-    }
-    if (vote_stats && tid == 0) {
-        atomicAdd(vote_stats + 2 * (blockIdx.x & 1023u), (unsigned long long)nh);
-        atomicAdd(vote_stats + 2 * (blockIdx.x & 1023u) + 1, (unsigned long long)total);
-    }
-    if (total < AID_MIN_VOTES) {
-        if (tid == 0) cand_n[out_slot] = 0;
-        return;
-    }
-    uint32_t R = (total + kGVotesPerRound - 1) / kGVotesPerRound;
-    bool direct = total <= kTableMaxLoad;        // few votes: they all fit the exact table, no sketch
-
-    for (;;) {                                        // restarted with a finer partition if the exact table fills
-        if (tid == 0) { sm.nbest = 0; sm.overflow = 0; }
-        for (uint32_t r = 0; r < R; r++) {
-            if (!direct) for (int i = tid; i < kGSketch / 8; i += kGThreads) reinterpret_cast<uint4*>(sm.sketch)[i] = make_uint4(0, 0, 0, 0);
-            for (int i = tid; i < kTable; i += kGThreads) {
-                sm.tkey[i] = kEmpty64; sm.tcnt[i] = 0; sm.tmin[i] = 0xffffffffu; sm.tmax[i] = 0;
-            }
-            if (tid == 0) { sm.used = 0; sm.hit = 0; sm.maybe = 0; }
-            __syncthreads();
-            for (int pass = direct ? 1 : 0; pass < 2; pass++) {
-                if (pass == 1 && !direct && !sm.maybe) break;       // no counter reached the threshold: nothing can have
-                for (uint32_t c0 = 0; c0 < nh; c0 += kGChunk) {
-                    const uint32_t nc = min((uint32_t)kGChunk, nh - c0);
-                    if (!single) stage(c0, nc);
-                    if (tid == 0) sm.next = 0;
-                    __syncthreads();
-                    for (;;) {                                       // warps take hashes as they become free
-                        uint32_t i = 0;
-                        if (lane == 0) i = atomicAdd(&sm.next, 1u);
-                        i = __shfl_sync(AID_FULL_MASK, i, 0);
-                        if (i >= nc) break;
-                        const uint32_t beg = sm.qbeg[i], qadd = sm.qadd[i];
-                        const uint4 c = sm.qcnt[i];
-                        const uint32_t e0 = c.x & 0xffffu, e1 = e0 + (c.x >> 16), e2 = e1 + (c.y & 0xffffu), e3 = e2 + (c.y >> 16),
-                                       e4 = e3 + (c.z & 0xffffu), e5 = e4 + (c.z >> 16), e6 = e5 + (c.w & 0xffffu), len = e6 + (c.w >> 16);
-                        for (uint32_t p = lane; p < len; p += 32) {
-                            const uint32_t post = postings[beg + p];
-                            const uint32_t sub = (p >= e0) + (p >= e1) + (p >= e2) + (p >= e3) + (p >= e4) + (p >= e5) + (p >= e6);
-                            if ((deleted_mask >> sub) & 1u) {
-                                const uint32_t local = post >> AID_POST_T_BITS;
-                                if (sm.tomb[sub][local >> 5] & (1u << (local & 31))) continue;
-                            }
-                            const uint32_t key = post + qadd;
-                            const uint32_t m = mix32(key ^ (sub * 0x9E3779B9u));
-                            if (R > 1 && (m >> 13) % R != r) continue;
-                            const uint32_t idx = m & (kGSketch - 1), sh = 16 * (idx & 1);
-                            if (pass == 0) {
-                                const uint32_t old = atomicAdd(&sm.sketch[idx >> 1], 1u << sh);
-                                if (((old >> sh) & 0xffffu) + 1 == AID_MIN_VOTES) sm.maybe = 1;
-                                continue;
-                            }
-                            if (!direct && ((sm.sketch[idx >> 1] >> sh) & 0xffffu) < AID_MIN_VOTES) continue;
-                            const unsigned long long k64 = ((unsigned long long)sub << 32) | key;
-                            const uint32_t tq = AID_QUERY_MAX_FRAMES - qadd;
-                            uint32_t slot = (m >> 20) & (kTable - 1);
-                            for (int probe = 0; probe < kTable; probe++) {
-                                const unsigned long long old = atomicCAS(&sm.tkey[slot], kEmpty64, k64);
-                                if (old == kEmpty64) { if (atomicAdd(&sm.used, 1u) >= kTableMaxLoad) sm.overflow = 1; }
-                                if (old == kEmpty64 || old == k64) {
-                                    if (atomicAdd(&sm.tcnt[slot], 1u) + 1 == AID_MIN_VOTES) sm.hit = 1;
-                                    atomicMin(&sm.tmin[slot], tq);
-                                    atomicMax(&sm.tmax[slot], tq);
-                                    break;
-                                }
-                                slot = (slot + 1) & (kTable - 1);
-                                if (probe == kTable - 1) sm.overflow = 1;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            if (sm.overflow) break;
-            if (!sm.hit) continue;
-            // ---- merge this round's exact counts into the running top-kBest: key = inverted 20-bit count | 35-bit vote key
-            const uint32_t nb = sm.nbest;
-            for (int i = tid; i < kSortN; i += kGThreads) {
-                uint64_t k = kPad; uint32_t v = 0;
-                if (i < kTable) {
-                    if (sm.tkey[i] != kEmpty64 && sm.tcnt[i] >= AID_MIN_VOTES) {
-                        k = ((uint64_t)(0xfffffu - min(sm.tcnt[i], 0xfffffu)) << 35) | sm.tkey[i];
-                        v = (sm.tmin[i] & 0xffffu) | (sm.tmax[i] << 16);
-                    }
-                } else if (i - kTable < (int)nb) { k = sm.bkey[i - kTable]; v = sm.bval[i - kTable]; }
-                sm.skey[i] = k; sm.sval[i] = v;
-            }
-            __syncthreads();
-            bitonic_sort<kSortN, kGThreads>(sm.skey, sm.sval, tid);
-            if (tid < kBest) { sm.bkey[tid] = sm.skey[tid]; sm.bval[tid] = sm.sval[tid]; }
-            if (tid == 0) {
-                uint32_t n = 0;
-                while (n < kBest && sm.skey[n] != kPad) n++;
-                sm.nbest = n;
-            }
-            __syncthreads();
-        }
-        __syncthreads();
-        if (!sm.overflow) break;
-        __syncthreads();
-        if (direct) direct = false; else R *= 2;
-    }
-
-    const uint32_t n = min(sm.nbest, (uint32_t)AID_MAX_ROWS);
-    CandEntry* out = cand + out_slot * AID_MAX_ROWS;
-    if (tid < (int)n) {
-        const uint64_t k = sm.bkey[tid];
-        CandEntry c;
-        c.inv_count = 0xffffffffu - (0xfffffu - (uint32_t)(k >> 35));          // the same encoding k_match writes
-        c.key = (uint32_t)k;
-        c.sub = (uint32_t)(k >> 32) & 7u;
-        c.tq = sm.bval[tid];
-        out[tid] = c;
-    }
-    if (tid == 0) cand_n[out_slot] = n;
+    if (tid == 0) cand_n[blockIdx.x] = n;
 }
 
 // ---- per query: merge the segments' lists, order by (count desc, track asc, offset asc), write rows
 constexpr int kRankN = 1024;
 
 __global__ void __launch_bounds__(kThreads)
-k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, const aid_unit_desc* __restrict__ segs,
+k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, const aid_seg_desc* __restrict__ segs,
        int n_seg, int max_rows, aid_match_row* __restrict__ rows, int32_t* __restrict__ n_rows, const RowSink sink) {
-    // (segs / n_seg are the match UNITS: plain segments and whole groups; a candidate of a group carries its member)
     __shared__ uint64_t skey[kRankN];
     __shared__ uint32_t sval[kRankN];       // index of the entry in cand
     __shared__ uint32_t s_fill, s_best;
@@ -546,7 +363,7 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
                 const int64_t ci = ((int64_t)q * n_seg + sg) * AID_MAX_ROWS + tid;
                 const CandEntry c = cand[ci];
                 const uint64_t inv = c.inv_count - (0xffffffffu - 0xfffffu);          // 20-bit inverted count
-                const uint64_t track = (uint64_t)segs[sg].first_track + c.sub * (uint32_t)AID_SEG_TRACKS + (c.key >> AID_POST_T_BITS);
+                const uint64_t track = (uint64_t)segs[sg].first_track + (c.key >> AID_POST_T_BITS);
                 const uint64_t off = c.key & ((1u << AID_POST_T_BITS) - 1);
                 skey[base + tid] = ((c.inv_count <= 0xffffffffu - 0xfffffu ? 0ull : inv) << 44) | (track << 19) | off;
                 sval[base + tid] = (uint32_t)ci;
@@ -573,7 +390,7 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
         const CandEntry c = cand[sval[tid]];
         const uint32_t sgi = (uint32_t)((sval[tid] / AID_MAX_ROWS) % n_seg);
         r.count = (int32_t)(0xffffffffu - c.inv_count);
-        r.track = segs[sgi].first_track + c.sub * (uint32_t)AID_SEG_TRACKS + (c.key >> AID_POST_T_BITS);
+        r.track = segs[sgi].first_track + (c.key >> AID_POST_T_BITS);
         r.offset = (int32_t)(c.key & ((1u << AID_POST_T_BITS) - 1)) - AID_QUERY_MAX_FRAMES;
         r.q_first = (int32_t)(c.tq & 0xffffu);
         r.q_last = (int32_t)(c.tq >> 16);
@@ -618,7 +435,7 @@ int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* 
     Index* ix = e->index;
     int rc = aid_index_commit_on(e, st);
     if (rc) return rc;
-    const int n_plain = ix->n_plain, n_groups = ix->n_group_units, n_seg = n_plain + n_groups;      // match units
+    const int n_seg = (int)ix->segs.size();
     if (n_q == 0) return AID_OK;
     if (n_seg == 0) {
         if (sink.lay.world == 0) { AID_CUDA(e, cudaMemsetAsync(d_n_rows, 0, (size_t)n_q * 4, st)); return AID_OK; }
@@ -641,19 +458,13 @@ int aid_match_device_out(aid_engine* e, const uint32_t* d_hash, const uint32_t* 
         stats = ix->vote_stats.as<unsigned long long>();
     }
     { StageTimer tm(e, st, 4);
-    if (n_groups > 0)
-        k_match_group<<<(unsigned)((int64_t)n_q * n_groups), kGThreads, 0, st>>>(
-            d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_groupdesc.as<aid_group_desc>(), n_groups, n_plain, n_seg,
-            ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), d_abort, stats);
-    if (n_plain > 0)
-        k_match<<<(unsigned)((int64_t)n_q * n_plain), kThreads, 0, st>>>(
-            d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_plaindesc.as<aid_seg_desc>(), n_plain, n_seg,
-            ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), d_abort, stats); }
+    k_match<<<(unsigned)n_cta, kThreads, 0, st>>>(d_hash, d_t, d_hash_off, d_hash_len, d_status, ix->d_segdesc.as<aid_seg_desc>(), n_seg,
+                                                  ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), d_abort, stats); }
     { StageTimer tm(e, st, 5);
-    k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_unitdesc.as<aid_unit_desc>(), n_seg,
+    k_rank<<<n_q, kThreads, 0, st>>>(ix->cand.as<CandEntry>(), ix->cand_n.as<uint32_t>(), ix->d_segdesc.as<aid_seg_desc>(), n_seg,
                                      max_rows, d_rows, d_n_rows, sink); }
     AID_CUDA(e, cudaGetLastError());
-    e->launches += 1 + (n_groups > 0) + (n_plain > 0);
+    e->launches += 2;
     return AID_OK;
 }
 

@@ -268,10 +268,6 @@ class Engine:
         """Full segments share a hash directory eight at a time (default) or keep one table each; rows are the same."""
         self._check(self._L.aid_index_set_grouping(self._h, int(bool(on))))
 
-    def index_set_group_matcher(self, on: bool) -> None:
-        """One vote CTA per (window, group) (default) or per (window, segment) everywhere; rows are the same."""
-        self._check(self._L.aid_index_set_group_matcher(self._h, int(bool(on))))
-
     def index_clear(self) -> None:
         self._check(self._L.aid_index_clear(self._h))
 

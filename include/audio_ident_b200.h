@@ -153,10 +153,6 @@ int aid_index_clear(aid_engine* e);
  * lengths) so that the eight CTAs probing them for a window share every directory sector and posting sector. Rows do
  * not depend on the grouping; on = 1 is the default, 0 keeps one table per segment (tests, A/B measurements). */
 int aid_index_set_grouping(aid_engine* e, int on);
-/* How grouped segments are voted on: on = 1 (default) one CTA per (window, GROUP) reads one directory entry per query
- * hash and walks the members' adjacent posting runs as one run (k_match_group); 0 = one CTA per (window, segment)
- * everywhere (the round-1 matcher; tests and A/B measurements). Rows are the same. */
-int aid_index_set_group_matcher(aid_engine* e, int on);
 /* out[8]: [0] live tracks, [1] postings, [2] segments, [3] tracks incl. deleted, [4] device bytes held by the index,
  * [5] segments that share a group directory */
 int aid_index_stats(aid_engine* e, int64_t* out);

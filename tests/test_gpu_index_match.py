@@ -206,12 +206,6 @@ def test_segment_groups_keep_rows_bit_exact(fresh_index, oracle, tmp_path):
     st = eng.index_stats()
     assert st["segments"] == 3 and st["segments_grouped"] == 2
     assert {int(x) for x in grouped[0]["track"][:4]} == {5, 20000, 39000, 39001} and ng[0] >= 4
-    # the group matcher (one CTA per window and GROUP, 64-bit vote keys) against the per-segment matcher on the same
-    # grouped index, and both against the oracle
-    eng.index_set_group_matcher(False)
-    per_seg, nps = check(ix)
-    eng.index_set_group_matcher(True)
-    assert np.array_equal(nps, ng) and all(np.array_equal(per_seg[i][:ng[i]], grouped[i][:ng[i]]) for i in range(len(picks)))
     eng.index_set_grouping(False)
     plain, npl = check(ix)
     assert eng.index_stats()["segments_grouped"] == 0
