@@ -113,22 +113,31 @@ def identify_stream(identifier, pcm, n_samples: int, window_s: float = 10.0, hop
         off = np.arange(len(starts) + 1, dtype=np.int64) * w
         merged, n = identifier.query(buf, off)
         m = np.asarray(merged.cpu().numpy() if hasattr(merged, "cpu") else merged); nn = np.asarray(n.cpu().numpy() if hasattr(n, "cpu") else n)
+    return _stitch(m, nn, starts, w, min_votes, offset_tol), m, nn, starts
+
+
+def _stitch(m: np.ndarray, nn: np.ndarray, starts: np.ndarray, w: int, min_votes: int, offset_tol: int) -> list[Segment]:
+    """Consecutive windows whose best row names the same track at (nearly) the same recording offset form one segment.
+    Definition (the loop this vectorises): a window continues the current segment iff its best row has >= min_votes,
+    the same track, and an offset within offset_tol frames of the segment's FIRST window."""
+    n = len(starts)
+    if n == 0:
+        return []
+    valid = (nn > 0) & (m[:, 0, 0] >= min_votes)
+    track = m[:, 0, 1]
+    off_rec = m[:, 0, 2] - starts // HOP                       # offset relative to the recording's frame axis
+    votes = m[:, 0, 0]
+    # candidate runs: maximal stretches of valid windows with one track (offsets are checked per run below)
+    same = valid[1:] & valid[:-1] & (track[1:] == track[:-1])
+    run_start = np.flatnonzero(valid & np.concatenate([[True], ~same]))
+    run_end = np.flatnonzero(valid & np.concatenate([~same, [True]])) + 1
     segs: list[Segment] = []
-    cur = None
-    for k, s in enumerate(starts):
-        best = m[k, 0] if nn[k] > 0 and m[k, 0, 0] >= min_votes else None
-        if best is not None:
-            track, off_rec = int(best[1]), int(best[2]) - int(s) // HOP      # offset relative to the recording's frame axis
-            if cur and cur.track == track and abs(cur.offset_frames - off_rec) <= offset_tol:
-                cur.stop_s = (s + w) / 16000.0; cur.votes += int(best[0]); cur.windows += 1
-                continue
-            if cur:
-                segs.append(cur)
-            cur = Segment(track, off_rec, s / 16000.0, (s + w) / 16000.0, int(best[0]), 1)
-        else:
-            if cur:
-                segs.append(cur)
-            cur = None
-    if cur:
-        segs.append(cur)
-    return segs, m, nn, starts
+    for a, b in zip(run_start, run_end):
+        k = int(a)
+        while k < b:                                           # split a run where the offset leaves the tolerance
+            drift = np.abs(off_rec[k:b] - off_rec[k]) > offset_tol
+            e = k + (int(np.argmax(drift)) if drift.any() else int(b - k))
+            segs.append(Segment(int(track[k]), int(off_rec[k]), float(starts[k]) / 16000.0, float(starts[e - 1] + w) / 16000.0,
+                                int(votes[k:e].sum()), e - k))
+            k = e
+    return segs

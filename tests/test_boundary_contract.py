@@ -145,6 +145,7 @@ def test_missing_engine_raises_olaf_error(monkeypatch):
 def test_window_ranges_equal_the_byte_slices():
     """exact_lane.plan_window_ranges (offsets into the clip, for the one-upload window query) describes exactly the
     byte strings plan_windows / the reference's _extract_pcm_window cut out (exact.py:374-399)."""
+    import numpy as np
     from audio_ident_b200 import exact_lane as xl
     rng = np.random.default_rng(0)
     for n in (0, 1, 15999, 16000, 23999, 24000, 24001, 56000, 67999, 68000, 79999, 80000, 80001, 200000):
