@@ -347,8 +347,12 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
     __shared__ uint32_t s_fill, s_best;
     const int tid = threadIdx.x, q = blockIdx.x;
     if (tid == 0) s_best = 0;
-    __syncthreads();
-    int sg = 0;
+    // Most windows have no candidate row in most shards (a query's track lives in one segment of one rank): count first and
+    // skip the fill / sort rounds -- two barriers per segment -- when there is nothing to rank.
+    uint32_t any = 0;
+    for (int s2 = tid; s2 < n_seg; s2 += kThreads) any |= cand_n[(int64_t)q * n_seg + s2];
+    const bool nothing = __syncthreads_or((int)any) == 0;
+    int sg = nothing ? n_seg : 0;
     while (sg < n_seg) {
         // keep the best kBest so far in slots [0, kBest), fill the rest from the next segments
         const uint32_t nbest = s_best;
@@ -409,7 +413,7 @@ k_rank(const CandEntry* __restrict__ cand, const uint32_t* __restrict__ cand_n, 
         if (tid < (int)n) sink.lay.rows(w, parity, sink.rank)[(int64_t)q * AID_MAX_ROWS + tid] = r;
         if (tid == 0) sink.lay.counts(w, parity, sink.rank)[q] = (int32_t)n;
     }
-    __threadfence_system();                       // this thread's peer stores are visible system-wide ...
+    if (tid < (int)n || tid == 0) __threadfence_system();     // the threads that stored to peers: their stores are visible system-wide ...
     __syncthreads();
     if (tid == 0) {
         const uint32_t prev = atomicAdd(sink.done, 1u);
