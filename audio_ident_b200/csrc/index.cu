@@ -583,15 +583,32 @@ extern "C" int aid_index_save(aid_engine* e, const char* dir) {
         const uint32_t len = (uint32_t)t.name.size(); const uint8_t del = t.deleted;
         good = good && wr(f, &len, 4) && wr(f, t.name.data(), len) && wr(f, &t.n_frames, 8) && wr(f, &t.n_hashes, 4) && wr(f, &del, 1);
     }
-    std::vector<uint32_t> buf;
+    // entries of deleted tracks are dropped on the way out (the track slots stay, so local numbers keep their meaning):
+    // a snapshot never carries tombstoned postings forward
+    std::vector<uint32_t> hb, pb;
+    uint64_t kept_total = 0;
     for (Segment* s : ix->segs) {
         const uint64_t n = (uint64_t)s->n_entries; const uint32_t nt = s->n_tracks;
-        good = good && wr(f, &nt, 4) && wr(f, &n, 8);
-        buf.resize((size_t)n);
-        for (DevBuf* src : {&s->st_hash, &s->st_post}) {
-            if (n && cudaMemcpy(buf.data(), src->p, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { fclose(f); return aid_fail_cuda(e, cudaGetLastError(), "save D2H"); }
-            good = good && wr(f, buf.data(), (size_t)n * 4);
+        hb.resize((size_t)n); pb.resize((size_t)n);
+        if (n && (cudaMemcpy(hb.data(), s->st_hash.p, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                  cudaMemcpy(pb.data(), s->st_post.p, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) {
+            fclose(f); return aid_fail_cuda(e, cudaGetLastError(), "save D2H");
         }
+        uint64_t kept = n;
+        if (s->n_deleted) {
+            kept = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                const uint32_t local = pb[(size_t)i] >> AID_POST_T_BITS;
+                if (s->h_tomb[local >> 5] & (1u << (local & 31))) continue;
+                hb[(size_t)kept] = hb[(size_t)i]; pb[(size_t)kept] = pb[(size_t)i]; kept++;
+            }
+        }
+        good = good && wr(f, &nt, 4) && wr(f, &kept, 8) && wr(f, hb.data(), (size_t)kept * 4) && wr(f, pb.data(), (size_t)kept * 4);
+        kept_total += kept;
+    }
+    if (good && kept_total != (uint64_t)ix->n_postings) {       // the header was written with the uncompacted count
+        h.n_postings = kept_total;
+        good = fseek(f, 0, SEEK_SET) == 0 && wr(f, &h, sizeof h) && fseek(f, 0, SEEK_END) == 0;
     }
     // durable before it replaces the old snapshot (the caller drops its journal right after): data, then the rename
     good = good && fflush(f) == 0 && fsync(fileno(f)) == 0;

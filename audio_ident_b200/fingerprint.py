@@ -97,6 +97,27 @@ def _journal_path(d: Path) -> Path:
     return d / "journal.bin"
 
 
+class _DirLock:
+    """Exclusive advisory lock on the index directory for the duration of a write (journal append, checkpoint): the
+    reference's LMDB is single-writer (fingerprint.py:7-8) and several service processes may share one directory."""
+
+    def __init__(self, d: Path) -> None:
+        self.path, self.fd = d / ".lock", None
+
+    def __enter__(self):
+        import fcntl
+        self.fd = os.open(str(self.path), os.O_CREAT | os.O_RDWR, 0o644)
+        fcntl.flock(self.fd, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        try:
+            fcntl.flock(self.fd, fcntl.LOCK_UN)
+        finally:
+            os.close(self.fd)
+
+
 def _replay_journal(eng, path: Path) -> int:
     """Re-applies the journal in order. Consecutive additions go to the engine as one batch (one ctypes call, one
     dirty-segment mark); a deletion or a repeated name flushes the batch so the order of effects is kept. The engine
@@ -166,7 +187,7 @@ def _append_journal(kind: int, name: str, n_frames: int = 0, h: np.ndarray | Non
         return
     nb = name.encode()
     n_hash = 0 if h is None else len(h)
-    with open(_journal_path(d), "ab") as f:
+    with _DirLock(d), open(_journal_path(d), "ab") as f:
         f.write(struct.pack("<4sIIqI", _JOURNAL_MAGIC, kind, len(nb), int(n_frames), n_hash))
         f.write(nb)
         if n_hash:
@@ -216,15 +237,16 @@ def checkpoint() -> None:
     with _state.lock:
         if _state.engine is None or _state.dir is None:
             return
-        _state.engine.index_save(str(_state.dir))      # data and rename are fsynced before this returns (aid_index_save)
-        jp = _journal_path(_state.dir)
-        if jp.exists():
-            jp.unlink()
-            try:
-                fd = os.open(str(_state.dir), os.O_RDONLY)
-                os.fsync(fd); os.close(fd)
-            except OSError:
-                pass
+        with _DirLock(_state.dir):
+            _state.engine.index_save(str(_state.dir))      # data and rename are fsynced before this returns (aid_index_save)
+            jp = _journal_path(_state.dir)
+            if jp.exists():
+                jp.unlink()
+                try:
+                    fd = os.open(str(_state.dir), os.O_RDONLY)
+                    os.fsync(fd); os.close(fd)
+                except OSError:
+                    pass
         _state.journal_bytes = 0
 
 

@@ -161,3 +161,21 @@ def test_damaged_journal_is_refused_not_uploaded(index_dir):
     assert rows and rows[0].reference_path == str(ia)                  # the record before the damage is there
     assert asyncio.run(fp.olaf_query(b[16000:16000 * 6].tobytes())) == []      # the damaged one and what follows are not
     assert asyncio.run(fp.olaf_query(c[16000:16000 * 6].tobytes())) == []
+
+
+def test_snapshot_drops_tombstoned_postings(index_dir):
+    """deletes are compacted away when a snapshot is written -- the postings of a deleted (or replaced)
+    track do not travel from snapshot to snapshot; results are unchanged."""
+    a, b = synth.make_track(900, 10.0), synth.make_track(901, 10.0)
+    ia, ib = uuid.uuid4(), uuid.uuid4()
+    assert asyncio.run(fp.index_tracks([(a.tobytes(), ia), (b.tobytes(), ib)])) == [True, True]
+    both = fp.get_engine().index_stats()["postings"]
+    assert asyncio.run(fp.olaf_delete_track(ia))
+    before = asyncio.run(fp.olaf_query(b[16000:16000 * 7].tobytes()))
+    fp.checkpoint()
+    assert (index_dir / ".lock").exists() and not (index_dir / "journal.bin").exists()
+    fp.shutdown()
+    st = fp.get_engine().index_stats()
+    assert 0 < st["postings"] < both and st["tracks"] == 1 and st["tracks_total"] == 2
+    assert asyncio.run(fp.olaf_query(b[16000:16000 * 7].tobytes())) == before
+    assert asyncio.run(fp.olaf_query(a[16000:16000 * 7].tobytes())) == []
