@@ -56,6 +56,7 @@ def load() -> C.CDLL:
         "aid_engine_sync": (C.c_int, [vp]),
         "aid_engine_set_max_batch_frames": (C.c_int, [vp, C.c_int64]),
         "aid_engine_set_stage_timing": (C.c_int, [vp, C.c_int]),
+        "aid_engine_set_kernels": (C.c_int, [vp, C.c_int, C.c_int]),
         "aid_engine_stage_times": (C.c_int, [vp, C.POINTER(C.c_double), i64p]),
         "aid_fingerprint_host": (C.c_int, [vp, vp, i64p, C.c_int, vp, vp, C.c_int64, i64p, i32p]),
         "aid_fingerprint_dev": (C.c_int, [vp, vp, i64p, C.c_int, C.POINTER(FpDeviceResult), vp]),
@@ -134,7 +135,7 @@ def load() -> C.CDLL:
 EXPORTED = [  # every symbol include/audio_ident_b200.h declares (tests/test_abi.py checks the header against this)
     "aid_abi_version", "aid_strerror", "aid_get_params", "aid_device_count", "aid_engine_create",
     "aid_engine_destroy", "aid_last_error", "aid_launch_count", "aid_engine_sync",
-    "aid_engine_set_max_batch_frames", "aid_engine_set_stage_timing", "aid_engine_stage_times", "aid_fingerprint_host", "aid_fingerprint_dev", "aid_stft_host",
+    "aid_engine_set_max_batch_frames", "aid_engine_set_stage_timing", "aid_engine_set_kernels", "aid_engine_stage_times", "aid_fingerprint_host", "aid_fingerprint_dev", "aid_stft_host",
     "aid_peaks_host", "aid_hashes_host", "aid_num_frames", "aid_index_add_host", "aid_index_add_host_fp", "aid_index_add_dev",
     "aid_index_add_hashes", "aid_index_delete", "aid_index_commit", "aid_index_clear", "aid_index_set_grouping", "aid_index_stats",
     "aid_index_track_name", "aid_index_save", "aid_index_load", "aid_query_host", "aid_query_dev", "aid_query_windows_host",

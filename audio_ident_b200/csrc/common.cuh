@@ -44,7 +44,9 @@ struct aid_tables {              // device-resident constant tables, built once 
     const float* twist;          // [AID_TWIST_FLOATS] twiddles between / inside the STFT transforms, see aid_fill_stft_tables
 };
 constexpr int AID_TWIST_FOLDED = 32 * 32;              // floats of the folded table
-constexpr int AID_TWIST_FLOATS = 32 * 32 + 32 * 64;    // + the plain table W_1024^(n1*k1)
+constexpr int AID_TWIST_IMAGE = 32 * 32 + 32 * 64;     // + the plain table W_1024^(n1*k1); then the shared-memory image of k_stft_packed
+constexpr int AID_TWIST_IMAGE_FLOATS = 2 * 32 * 36;    // [32][36] window / 2, lane-major, then [32][36] packed twiddles (stft.cu)
+constexpr int AID_TWIST_FLOATS = AID_TWIST_IMAGE + AID_TWIST_IMAGE_FLOATS;
 
 // Host-side definition of the two tables (double precision, rounded to float once).
 //  window[n] : symmetric Hamming, the formula of oracle/aid_oracle.c tables_init.
@@ -52,6 +54,10 @@ constexpr int AID_TWIST_FLOATS = 32 * 32 + 32 * 64;    // + the plain table W_10
 //    i = 0: stage 0 (m 16, h 1, k 0)      i = 1: stage 1 (m 8, h 2, k 0)      i = 2..3: stage 2 (m 4, h 4, k 0..1)
 //    i = 4..7: stage 3 (m 2, h 8, k 0..3)  i = 8..15: stage 4 (m 1, h 16, k 0..7)
 //  twist[1024 + k1*64 + 2*n1], [+1] = (c, s) of W_1024^(n1*k1) = c - i s: the inter-transform twiddle itself.
+//  twist[AID_TWIST_IMAGE ...]: the two tables as k_stft_packed keeps them in shared memory (copied with 128-bit loads):
+//    [lane][j], j < 32 (row stride 36): window[lane + 32 j] / 2 (exact);
+//    [k1][4 e + w] (row stride 36): the folded twiddles of the same values, two butterflies per quad: e = 0: stage 1 as
+//    (c, -s, s, c); e >= 1: twiddles i = 2e, 2e + 1 of the list above as (c_i, c_i+1, s_i, s_i+1); [k1][32..33]: stage 0 (c, s).
 inline void aid_fill_stft_tables(float* window, float* twist) {
     const double two_pi = 6.283185307179586476925286766559;
     for (int i = 0; i < AID_NFFT; i++)
@@ -72,12 +78,28 @@ inline void aid_fill_stft_tables(float* window, float* twist) {
             twist[AID_TWIST_FOLDED + k1 * 64 + 2 * n1 + 1] = (float)sin(a);
         }
     }
+    float* img_win = twist + AID_TWIST_IMAGE;
+    float* img_tw = img_win + 32 * 36;
+    for (int i = 0; i < 2 * 32 * 36; i++) img_win[i] = 0.0f;
+    for (int i = 0; i < AID_NFFT; i++) img_win[(i & 31) * 36 + (i >> 5)] = 0.5f * window[i];
+    for (int k1 = 0; k1 < 32; k1++) {
+        const float* t = twist + k1 * 32;
+        float* o = img_tw + k1 * 36;
+        o[0] = t[2]; o[1] = -t[3]; o[2] = t[3]; o[3] = t[2];
+        for (int e = 1; e < 8; e++)
+            for (int w = 0; w < 4; w++) o[4 * e + w] = w < 2 ? t[2 * (2 * e + w)] : t[2 * (2 * e + w - 2) + 1];
+        o[32] = t[0]; o[33] = t[1];
+    }
 }
 
-cudaError_t aid_launch_stft(const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
-                            int n_units, float* d_spec, cudaStream_t st);
+// variant: 0 = scalar FP32 kernel (round 1), 7 = packed f32x2 kernel, software-pipelined, with L1 prefetch (default; other
+// values are A/B shapes, see stft.cu). d_gmax (nullable, packed variants only): [rows][32] group maxima for the peak kernel.
+cudaError_t aid_launch_stft_variant(int variant, const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
+                                    int n_units, float* d_spec, float* d_gmax, cudaStream_t st);
+int aid_stft_default_variant();      // 7, or the environment's AID_STFT_VARIANT (measurement runs)
 
-cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, const aid_peak_run* d_runs,
+// d_gmax (nullable): the STFT's group maxima; with it the peak kernel streams 128 B per row instead of the 2 KB row
+cudaError_t aid_launch_peaks(const float* d_spec, const float* d_gmax, const aid_peak_unit* d_units, const aid_peak_run* d_runs,
                              int n_runs, uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
                              cudaStream_t st);
 

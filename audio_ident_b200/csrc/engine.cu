@@ -5,6 +5,7 @@
 #include <string.h>
 #include <algorithm>
 #include "engine.h"
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------ library
 extern "C" int aid_abi_version(void) { return AID_ABI_VERSION; }
@@ -55,7 +56,7 @@ int aid_fail_cuda(aid_engine* e, cudaError_t ce, const char* what) {
 
 // ------------------------------------------------------------------------------------------- engine
 void Slot::release() {
-    DevBuf* bufs[] = {&pcm, &desc, &spec, &slots, &unit_pos, &peaks, &peak_track, &peak_off, &pos, &hash, &t,
+    DevBuf* bufs[] = {&pcm, &desc, &spec, &gmax, &slots, &unit_pos, &peaks, &peak_track, &peak_off, &pos, &hash, &t,
                       &hash_off, &status, &scan_tmp, &misc};
     for (DevBuf* b : bufs) b->release();
     h_desc.release(); h_small.release();
@@ -70,6 +71,8 @@ extern "C" int aid_engine_create(int device, aid_engine** out) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return AID_E_CUDA; }
     aid_engine* e = new aid_engine();
+    e->stft_variant = aid_stft_default_variant();
+    if (const char* v = getenv("AID_PEAK_SUMMARY")) e->peak_summary = atoi(v) != 0;     // measurement runs
     e->device = device;
     auto fail = [&](cudaError_t ce, const char* what) { int r = aid_fail_cuda(e, ce, what); fprintf(stderr, "audio_ident_b200: %s\n", e->err.c_str()); aid_engine_destroy(e); return r; };
     cudaError_t ce;
@@ -195,6 +198,7 @@ int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, in
     const size_t n = (size_t)plan.n_tracks, nu = plan.punits.size();
     if (need_pcm) AID_CUDA(e, s.pcm.ensure((size_t)std::max<int64_t>(pcm_samples, 1) * sizeof(float)));
     AID_CUDA(e, s.spec.ensure((size_t)std::max<int64_t>(plan.total_frames, 1) * AID_NBINS * sizeof(float)));
+    AID_CUDA(e, s.gmax.ensure((size_t)std::max<int64_t>(plan.total_frames, 1) * 32 * sizeof(float)));
     AID_CUDA(e, s.slots.ensure((size_t)std::max<int64_t>(plan.peak_cap, 1) * sizeof(uint32_t)));
     AID_CUDA(e, s.unit_pos.ensure((nu + 1) * 2 * sizeof(uint32_t)));           // counts, then positions
     AID_CUDA(e, s.peaks.ensure((size_t)(plan.peak_cap + 1) * sizeof(uint32_t)));
@@ -218,6 +222,13 @@ int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, in
     s.d_punits = reinterpret_cast<aid_peak_unit*>(s.desc.as<char>() + b0);
     s.d_first_punit = reinterpret_cast<uint32_t*>(s.desc.as<char>() + b0 + b1);
     s.d_pruns = reinterpret_cast<aid_peak_run*>(s.desc.as<char>() + b0 + b1 + b2);
+    return AID_OK;
+}
+
+extern "C" int aid_engine_set_kernels(aid_engine* e, int stft_variant, int peak_summary) {
+    if (!e || stft_variant < 0 || stft_variant > 15) return AID_E_ARG;
+    e->stft_variant = stft_variant;
+    e->peak_summary = peak_summary != 0;
     return AID_OK;
 }
 
@@ -264,10 +275,11 @@ int aid_run_fingerprint(aid_engine* e, Slot& s, const Plan& plan, const float* d
     uint32_t* unit_cnt = s.unit_pos.as<uint32_t>();
     uint32_t* unit_pos = unit_cnt + (npu + 1);
     uint32_t* misc = s.misc.as<uint32_t>();
+    float* gmax = e->peak_summary && e->stft_variant != 0 ? s.gmax.as<float>() : nullptr;
     { StageTimer tm(e, st, 0);
-      AID_CUDA(e, aid_launch_stft(e->tables, d_pcm, s.d_sunits, nsu, s.spec.as<float>(), st)); }
+      AID_CUDA(e, aid_launch_stft_variant(e->stft_variant, e->tables, d_pcm, s.d_sunits, nsu, s.spec.as<float>(), gmax, st)); }
     { StageTimer tm(e, st, 1);
-      AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, s.d_pruns, (int)plan.pruns.size(),
+      AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), gmax, s.d_punits, s.d_pruns, (int)plan.pruns.size(),
                                    s.slots.as<uint32_t>(), unit_cnt, s.status.as<int32_t>(), st)); }
     // unit counts -> dense positions (unit_pos[npu] = total peaks)
     { StageTimer tm2(e, st, 2);
@@ -474,7 +486,7 @@ extern "C" int aid_stft_host(aid_engine* e, const float* pcm, const int64_t* sam
     if (!pcm || !spec) return AID_E_ARG;
     AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + sample_off[0], (size_t)samples * sizeof(float), cudaMemcpyHostToDevice, s.st));
     AID_CUDA(e, cudaMemcpyAsync(s.desc.p, plan.sunits.data(), plan.sunits.size() * sizeof(aid_stft_unit), cudaMemcpyHostToDevice, s.st));
-    AID_CUDA(e, aid_launch_stft(e->tables, s.pcm.as<float>(), s.d_sunits, (int)plan.sunits.size(), s.spec.as<float>(), s.st));
+    AID_CUDA(e, aid_launch_stft_variant(e->stft_variant, e->tables, s.pcm.as<float>(), s.d_sunits, (int)plan.sunits.size(), s.spec.as<float>(), nullptr, s.st));
     e->launches += 1;
     AID_CUDA(e, cudaMemcpyAsync(spec, s.spec.p, (size_t)plan.total_frames * AID_NBINS * sizeof(float), cudaMemcpyDeviceToHost, s.st));
     AID_CUDA(e, cudaStreamSynchronize(s.st));
@@ -514,7 +526,7 @@ extern "C" int aid_peaks_host(aid_engine* e, const float* spec, const int64_t* f
     AID_CUDA(e, cudaMemsetAsync(s.status.p, 0, (size_t)(n + 1) * sizeof(int32_t), s.st));
     uint32_t* unit_cnt = s.unit_pos.as<uint32_t>();
     uint32_t* unit_pos = unit_cnt + (npu + 1);
-    AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), s.d_punits, s.d_pruns, (int)plan.pruns.size(), s.slots.as<uint32_t>(), unit_cnt, s.status.as<int32_t>(), s.st));
+    AID_CUDA(e, aid_launch_peaks(s.spec.as<float>(), nullptr, s.d_punits, s.d_pruns, (int)plan.pruns.size(), s.slots.as<uint32_t>(), unit_cnt, s.status.as<int32_t>(), s.st));
     AID_CUDA(e, cudaMemsetAsync(unit_cnt + npu, 0, sizeof(uint32_t), s.st));
     AID_CUDA(e, aid_launch_scan_u32(unit_cnt, unit_pos, npu + 1, s.scan_tmp.as<uint32_t>(), nullptr, nullptr, s.st));
     AID_CUDA(e, aid_launch_peak_compact(s.slots.as<uint32_t>(), unit_cnt, unit_pos, s.d_punits, npu, s.peaks.as<uint32_t>(), s.peak_track.as<uint32_t>(), s.st));

@@ -57,7 +57,7 @@ struct Plan {
 struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf pcm, desc, spec, slots, unit_pos, peaks, peak_track, peak_off, pos, hash, t, hash_off, status,
+    DevBuf pcm, desc, spec, gmax, slots, unit_pos, peaks, peak_track, peak_off, pos, hash, t, hash_off, status,
            scan_tmp, misc;
     PinBuf h_desc, h_small;
     // views into `desc` (one upload per sub-batch)
@@ -79,6 +79,9 @@ struct aid_engine {
     DevBuf d_window, d_twiddle;
     aid_tables tables{};
     Index* index = nullptr;
+    // kernel selection (aid_engine_set_kernels; the defaults are the product path, the others exist for tests and A/B runs)
+    int stft_variant = 7;        // stft.cu aid_launch_stft_variant: 0 = scalar FP32 kernel, 7 = packed f32x2 kernel
+    bool peak_summary = true;    // the STFT also writes the 16-bin group maxima and the peak kernel streams those
     // optional per-stage timing (aid_engine_set_stage_timing)
     bool timing = false;
     struct StageRec { int stage; cudaEvent_t a, b; };

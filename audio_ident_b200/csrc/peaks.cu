@@ -46,6 +46,9 @@ struct WarpSmem {
     uint32_t buf[kBuf];
 };
 
+constexpr int kStage = 16;                  // summary rows in flight per warp (SUMMARY kernels only)
+template <bool SUMMARY> struct WarpSmemT : WarpSmem { float stage[SUMMARY ? kStage : 1][32]; };
+
 // The window bins of (row, f) that lie outside the whole groups, tested exactly against v.
 // i = f & 15, g = f >> 4. Whole groups inside the window: g-2..g+2, plus g-3 if i <= 3, plus g+3 if i >= 12;
 // that leaves at most 15 bins on each side, and each side lies inside ONE aligned group (the left edge ends, the right
@@ -109,6 +112,14 @@ struct Stream {             // per-warp state (the same in every lane except px)
     float px;               // per lane: max of C5 over those rows
 };
 
+// C5 = max(A[g-2 .. g+2]) from the lane's own group maximum
+__device__ __forceinline__ float five_group_max(float A) {
+    // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
+    const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
+    const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
+    return fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
+}
+
 // Row pass, register part: group maximum A and 5-group maximum C5 of one row loaded by load_row_stream. Pure
 // register/shuffle code, so the two rows of a trip can be interleaved by the scheduler. The four partial maxima of a
 // lane belong to four groups; a 4 x 4 transpose-reduce inside each quad of lanes (3 shuffles) leaves lane 4 j + p with
@@ -125,13 +136,11 @@ __device__ __forceinline__ void row_reduce(const float4 (&x)[4], float& A, float
     const float c = fmaxf(hi ? b1 : b0, r3);
     const int q = lane >> 3;                                 // this lane's group is 8 q + (lane & 7)
     A = __shfl_sync(AID_FULL_MASK, c, 4 * (lane & 7) + ((q >> 1) | ((q & 1) << 1)));
-    // out-of-range shuffles return the lane's own A, which never changes a maximum that already contains A
-    const float am1 = __shfl_up_sync(AID_FULL_MASK, A, 1), am2 = __shfl_up_sync(AID_FULL_MASK, A, 2);
-    const float ap1 = __shfl_down_sync(AID_FULL_MASK, A, 1), ap2 = __shfl_down_sync(AID_FULL_MASK, A, 2);
-    c5 = fmaxf(fmaxf(fmaxf(A, am1), fmaxf(am2, ap1)), ap2);
+    c5 = five_group_max(A);
 }
 
 // Row pass, ring part: van Herk block bookkeeping, A / C5 / candidate flag into the rings.
+template <bool PREFETCH = false>
 __device__ __forceinline__ void row_commit(WarpSmem& sm, Stream& st, float A, float c5, int r, int lane) {
     if (st.jb == kBlock) {                                   // the previous 25-row block is complete: turn its C5
         float sfx = -1.0f;                                   // entries into suffix maxima, start a new block
@@ -148,6 +157,10 @@ __device__ __forceinline__ void row_commit(WarpSmem& sm, Stream& st, float A, fl
     st.px = fmaxf(st.px, c5);
     const int slot = r & (kRing - 1);
     const bool cand = r >= st.row0 && r < st.row_end && A == c5 && A > AID_PEAK_MIN_S;
+    if constexpr (PREFETCH) {      // summary mode never streamed the row: a candidate group's 16 bins (what verify_row reads 12 rows
+        if (cand)                  // later if the candidate survives the column pass) are pulled towards the L2 now
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(st.base + (int64_t)r * AID_NBINS + 16 * lane));
+    }
     sm.A[slot][lane] = cand ? -A : A;
     sm.C5[slot][lane] = c5;
 }
@@ -271,10 +284,18 @@ __device__ __forceinline__ void verify_row(WarpSmem& sm, Stream& st, int c, int 
 #ifndef AID_PEAKS_MIN_CTAS
 #define AID_PEAKS_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(kWarpsPerCta * 32, AID_PEAKS_MIN_CTAS)
-k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units, const aid_peak_run* __restrict__ runs,
-        int n_runs, uint32_t* __restrict__ slots, uint32_t* __restrict__ unit_count, int32_t* __restrict__ track_status) {
-    __shared__ WarpSmem s_all[kWarpsPerCta];
+// SUMMARY: the group maxima come from the STFT kernel (gmax[row][32], stft.cu GroupMax) instead of the row itself: the warp
+// streams 128 B per row, four rows per trip with the next four in flight, and touches the spectrogram only where a
+// candidate survives (verify_row). Same rings, same column pass, same settlement: the peaks are bit-identical.
+#ifndef AID_PEAKS_SUM_CTAS
+#define AID_PEAKS_SUM_CTAS 5
+#endif
+template <bool SUMMARY>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, SUMMARY ? AID_PEAKS_SUM_CTAS : AID_PEAKS_MIN_CTAS)
+k_peaks(const float* __restrict__ spec, const float* __restrict__ gmax, const aid_peak_unit* __restrict__ units,
+        const aid_peak_run* __restrict__ runs, int n_runs, uint32_t* __restrict__ slots, uint32_t* __restrict__ unit_count,
+        int32_t* __restrict__ track_status) {
+    __shared__ WarpSmemT<SUMMARY> s_all[kWarpsPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int run_id = blockIdx.x * kWarpsPerCta + warp;
     if (run_id >= n_runs) return;
@@ -298,6 +319,38 @@ k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
     st.jb = 0;
     st.px = -1.0f;
 
+    if constexpr (SUMMARY) {
+        // ONE row per trip of ONE loop (commit row r, verify row r - 12; the rows past the end of the track only verify),
+        // so the kernel holds a single copy of the column pass and the settlement: with them inlined once per row of a
+        // four-row trip the kernel was 43 KB of code and stalled on instruction fetch (9.6 "no instruction" stall cycles
+        // per issued instruction, profiles/r02_peaks_summary.md). A row is one 128 B line per warp, so it is latency, not
+        // bandwidth, that has to be covered: the next kStage rows are in flight as cp.async copies into a small ring
+        // (cp.async.wait_group counts GROUPS, so waiting for the oldest copy does not wait for the newest -- a register
+        // ring filled by one LDG in a rolled loop does: all its loads share one counted scoreboard).
+        const float* g = gmax + u.spec_row0 * 32 + lane;     // this lane's column of the summary
+        float (*stage)[32] = s_all[warp].stage;
+        auto fetch = [&](int row) {                          // this lane's value of `row` -> its slot (clamped: keeps the groups uniform)
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[row & (kStage - 1)][lane]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(g + (int64_t)min(row, st.hi - 1) * 32) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int k = 0; k < kStage; k++) fetch(st.lo + k);
+        const int r_end = st.row_end + kHalfT;               // the last row verified is row_end - 1
+#pragma unroll 1
+        for (int r = st.lo; r < r_end; r++) {
+            if (r < st.hi) {
+                asm volatile("cp.async.wait_group %0;" :: "n"(kStage - 1) : "memory");
+                const float a = stage[r & (kStage - 1)][lane];
+                fetch(r + kStage);
+                row_commit<true>(sm, st, a, five_group_max(a), r, lane);
+            }
+            const int c = r - kHalfT;
+            if (c >= st.row0) verify_row(sm, st, c, min(r, st.hi - 1), lane);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        flush_block(sm, st, lane);
+        return;
+    } else {
     // two rows per trip, the next two already in flight
     float4 na[4], nb[4];
     load_row_stream(na, st.base + (int64_t)st.lo * AID_NBINS, lane);
@@ -318,6 +371,7 @@ k_peaks(const float* __restrict__ spec, const aid_peak_unit* __restrict__ units,
             row_commit(sm, st, A1, c1, r + 1, lane);
             if (r + 1 - kHalfT >= st.row0) verify_row(sm, st, r + 1 - kHalfT, r + 1, lane);
         }
+    }
     }
     // rows whose window is cut by the end of the track
     for (int c = max(st.row0, st.hi - kHalfT); c < st.row_end; c++) verify_row(sm, st, c, st.hi - 1, lane);
@@ -340,12 +394,13 @@ __global__ void k_peak_compact(const uint32_t* __restrict__ slots, const uint32_
 
 }  // namespace
 
-cudaError_t aid_launch_peaks(const float* d_spec, const aid_peak_unit* d_units, const aid_peak_run* d_runs,
+cudaError_t aid_launch_peaks(const float* d_spec, const float* d_gmax, const aid_peak_unit* d_units, const aid_peak_run* d_runs,
                              int n_runs, uint32_t* d_slots, uint32_t* d_unit_count, int32_t* d_track_status,
                              cudaStream_t st) {
     if (n_runs <= 0) return cudaSuccess;
     const int grid = (n_runs + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_peaks<<<grid, kWarpsPerCta * 32, 0, st>>>(d_spec, d_units, d_runs, n_runs, d_slots, d_unit_count, d_track_status);
+    if (d_gmax) k_peaks<true><<<grid, kWarpsPerCta * 32, 0, st>>>(d_spec, d_gmax, d_units, d_runs, n_runs, d_slots, d_unit_count, d_track_status);
+    else k_peaks<false><<<grid, kWarpsPerCta * 32, 0, st>>>(d_spec, nullptr, d_units, d_runs, n_runs, d_slots, d_unit_count, d_track_status);
     return cudaGetLastError();
 }
 

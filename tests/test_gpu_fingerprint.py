@@ -203,3 +203,70 @@ def test_device_resident_path_equals_host_path(engine):
     finally:
         engine.device_free(d)
     assert np.array_equal(doff.astype(np.int64), hoff) and np.array_equal(dh, h) and np.array_equal(dt, t)
+
+
+# ---- kernel selection (aid_engine_set_kernels): every choice must give the same bits ----------------------------------
+
+def _ragged_mix():
+    rng = np.random.default_rng(77)
+    clips = [synth.make_track(400 + k, s) for k, s in enumerate([0.07, 0.2, 1.0, 2.04, 3.5, 8.19, 8.2, 16.4, 33.0])]
+    clips += [rng.uniform(-1, 1, n).astype(np.float32) for n in (1024, 1151, 1152, 1280, 4095, 9343, 9344)]
+    clips += [np.zeros(0, np.float32), np.zeros(700, np.float32), np.zeros(5000, np.float32)]
+    return ragged(clips)
+
+
+def test_packed_stft_kernel_is_bit_identical_to_the_scalar_one(engine):
+    """csrc/stft.cu: k_stft_packed (f32x2 instructions, the default) performs the scalar kernel's operations on every
+    element in the same order, so the stored spectrogram must not differ in a single bit (odd and even frame counts,
+    units of fewer than 64 frames, tracks shorter than one unit)."""
+    pcm, off = _ragged_mix()
+    try:
+        engine.set_kernels(0, False)
+        ref = engine.stft(pcm, off)
+        for variant in (7, 5, 3, 1, 15):
+            engine.set_kernels(variant, False)
+            got = engine.stft(pcm, off)
+            assert ref.shape == got.shape
+            assert np.array_equal(ref.view(np.uint32), got.view(np.uint32)), f"variant {variant}"
+    finally:
+        engine.set_kernels(7, True)
+
+
+def test_peak_summary_path_gives_the_same_fingerprints(engine):
+    """The STFT kernel's group maxima (peak_summary, default) feed the peak kernel instead of the spectrogram rows:
+    hashes, anchors, offsets and status words must be identical to the row-streaming path and to the round-1 kernels,
+    also across sub-batches."""
+    pcm, off = _ragged_mix()
+    try:
+        engine.set_kernels(0, False)
+        ref = engine.fingerprint(pcm, off)
+        for variant, summary in ((7, False), (7, True), (5, True)):
+            engine.set_kernels(variant, summary)
+            got = engine.fingerprint(pcm, off)
+            for x, y in zip(ref, got):
+                assert np.array_equal(x, y), (variant, summary)
+        engine.set_kernels(7, True)
+        engine.set_max_batch_frames(700)
+        got = engine.fingerprint(pcm, off)
+        for x, y in zip(ref, got):
+            assert np.array_equal(x, y)
+    finally:
+        engine.set_max_batch_frames(8 * 1024 * 1024)
+        engine.set_kernels(7, True)
+
+
+def test_peak_summary_path_with_exact_ties(engine, oracle):
+    """Plateaus of exactly equal values (every member of a tie is a peak) through the summary path: a stepped chirp whose
+    spectrogram the oracle also sees; peaks are compared on the GPU's own spectrogram."""
+    x = synth.make_track(901, 12.0)
+    x[16000:48000] = 0.0                                   # silence: S = 0 everywhere, below the gate
+    x[64000:96000] = x[32000 + 64000:64000 + 64000]
+    try:
+        engine.set_kernels(7, True)
+        h1 = engine.fingerprint(x, [0, len(x)])
+        S = engine.stft(x, [0, len(x)])
+        pk, _, _ = engine.peaks(S, [0, S.shape[0]])       # row-streaming peak kernel on the same spectrogram
+        rh, rt = oracle.hashes(pk)
+        assert np.array_equal(h1[0], rh) and np.array_equal(h1[1], rt)
+    finally:
+        engine.set_kernels(7, True)

@@ -101,6 +101,30 @@ __global__ void __launch_bounds__(512, 1) k(float* out, long long* cyc, float se
                     asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(A[i]) : "l"(B[i]), "l"(C));
                     asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(A[i + 1]) : "l"(B[i + 1]));
                 }
+        } else if (MODE == 13) {  // blocks: 16 FFMA2 then 16 scalar FFMA (the packed STFT's shape: packed stages, one scalar stage)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(A[i]) : "l"(B[i]), "l"(C));
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(a[i]) : "f"(b[i]), "f"(c));
+        } else if (MODE == 14) {  // FFMA2 with a broadcast immediate multiplier
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("{.reg .b64 t; mov.b64 t, {0f3F7FF000, 0f3F7FF000}; fma.rn.f32x2 %0, %1, t, %0;}" : "+l"(A[i]) : "l"(B[i]));
+        } else if (MODE == 15) {  // FFMA2 + scalar FFMA 2:2 (scalar instructions in adjacent pairs)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) {
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(A[i]) : "l"(B[i]), "l"(C));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(A[i + 1]) : "l"(B[i + 1]), "l"(C));
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(a[i + 2]) : "f"(b[i + 2]), "f"(c));
+                    asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(a[i + 3]) : "f"(b[i + 3]), "f"(c));
+                }
         } else if (MODE == 12) {  // FFMA2 + MUFU.LG2 7:1
 #pragma unroll
             for (int r = 0; r < 4; r++) {
@@ -144,6 +168,7 @@ int main() {
         run<3>("FADD", threads); run<4>("FADD2", threads); run<5>("FMUL", threads); run<6>("FMUL2", threads);
         run<7>("FFMA+FADD 1:1", threads); run<8>("FFMA2+SHFL 3:1", threads); run<9>("FFMA+SHFL 3:1", threads);
         run<10>("FFMA2+FFMAimm 1:1", threads); run<11>("FFMA2+FADD2 1:1", threads); run<12>("FFMA2+LG2 7:1", threads);
+        run<13>("16 FFMA2 | 16 FFMA blocks", threads); run<14>("FFMA2 imm", threads); run<15>("FFMA2+FFMA 2:2", threads);
     }
     return 0;
 }

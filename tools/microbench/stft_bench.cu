@@ -1,6 +1,7 @@
 // stft_bench.cu -- A/B timing and a double-precision spot check of k_stft, outside the engine.
 // Build (tools/microbench/build.sh): compiles audio_ident_b200/csrc/stft.cu with -DAID_STFT_BENCH_VARIANT flags
-// Usage: stft_bench [tracks=2048] [seconds=30] [reps=5]
+// Usage: stft_bench [tracks=2048] [seconds=30] [reps=5] [variant=1]   (variant 0: scalar k_stft, 1: packed f32x2 k_stft_packed;
+//        a variant other than 0 is also compared bit for bit with variant 0 over the whole spectrogram)
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -18,12 +19,32 @@ __global__ void k_fill(float* p, int64_t n, uint32_t seed) {
     }
 }
 
+// every entry of gmax must be the exact maximum of its 16-bin group of the stored row
+__global__ void k_check_gmax(const float* spec, const float* gmax, int64_t rows, unsigned long long* cnt) {
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows * 32; i += (int64_t)gridDim.x * blockDim.x) {
+        const float* g = spec + (i >> 5) * AID_NBINS + (i & 31) * 16;
+        float m = g[0];
+        for (int k = 1; k < 16; k++) m = fmaxf(m, g[k]);
+        c += __float_as_uint(m) != __float_as_uint(gmax[i]);
+    }
+    if (c) atomicAdd(cnt, c);
+}
+
+__global__ void k_diff(const uint32_t* a, const uint32_t* b, int64_t n, unsigned long long* cnt) {
+    unsigned long long c = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += a[i] != b[i];
+    if (c) atomicAdd(cnt, c);
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 int main(int argc, char** argv) {
     const int tracks = argc > 1 ? atoi(argv[1]) : 2048;
     const double seconds = argc > 2 ? atof(argv[2]) : 30.0;
     const int reps = argc > 3 ? atoi(argv[3]) : 5;
+    const int variant = argc > 4 ? atoi(argv[4]) : 7;
+    const int with_gmax = argc > 5 ? atoi(argv[5]) : 0;      // 1: the kernel also writes the group maxima (checked against the rows)
     const int64_t ns = (int64_t)(seconds * 16000.0);
     const int64_t T = (ns - AID_NFFT) / AID_HOP + 1;
     std::vector<aid_stft_unit> units;
@@ -40,23 +61,44 @@ int main(int argc, char** argv) {
     aid_fill_stft_tables(win.data(), tw.data());
     CK(cudaMalloc(&d_win, 4096)); CK(cudaMalloc(&d_tw, tw.size() * 4));
     CK(cudaMemcpy(d_win, win.data(), 4096, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_tw, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
+    float* d_gmax = nullptr;
+    if (with_gmax && variant != 0) CK(cudaMalloc(&d_gmax, (size_t)tracks * T * 32 * 4));
     k_fill<<<148 * 8, 256>>>(d_pcm, tracks * ns, 12345u);
     CK(cudaDeviceSynchronize());
     aid_tables tb{d_win, d_tw};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int w = 0; w < 2; w++) CK(aid_launch_stft(tb, d_pcm, d_units, (int)units.size(), d_spec, 0));
+    for (int w = 0; w < 2; w++) CK(aid_launch_stft_variant(variant, tb, d_pcm, d_units, (int)units.size(), d_spec, d_gmax, 0));
     CK(cudaDeviceSynchronize());
     float best = 1e9f, sum = 0;
     for (int r = 0; r < reps; r++) {
         cudaEventRecord(e0);
-        CK(aid_launch_stft(tb, d_pcm, d_units, (int)units.size(), d_spec, 0));
+        CK(aid_launch_stft_variant(variant, tb, d_pcm, d_units, (int)units.size(), d_spec, d_gmax, 0));
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); sum += ms;
     }
     const double bytes = (double)tracks * ns * 4 + (double)tracks * T * AID_NBINS * 4;
+    printf("variant %d: ", variant);
     printf("k_stft %d tracks x %.0f s: best %.3f ms avg %.3f ms  -> %.1f GB/s algorithmic = %.1f %% of 6558.4\n", tracks, seconds,
            best, sum / reps, bytes / (sum / reps) * 1e-6, bytes / (sum / reps) * 1e-6 / 6558.4 * 100.0);
 
+    if (variant != 0) {          // bit-for-bit against the scalar kernel
+        float* d_ref; unsigned long long* d_cnt; unsigned long long h_cnt = 0;
+        const int64_t n = (int64_t)tracks * T * AID_NBINS;
+        CK(cudaMalloc(&d_ref, n * 4)); CK(cudaMalloc(&d_cnt, 8)); CK(cudaMemset(d_cnt, 0, 8));
+        CK(aid_launch_stft_variant(0, tb, d_pcm, d_units, (int)units.size(), d_ref, nullptr, 0));
+        k_diff<<<148 * 8, 256>>>((const uint32_t*)d_spec, (const uint32_t*)d_ref, n, d_cnt);
+        CK(cudaMemcpy(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost));
+        printf("bitwise vs variant 0: %llu of %lld values differ\n", h_cnt, (long long)n);
+        cudaFree(d_ref); cudaFree(d_cnt);
+    }
+    if (d_gmax) {
+        unsigned long long* d_cnt; unsigned long long h_cnt = 0;
+        CK(cudaMalloc(&d_cnt, 8)); CK(cudaMemset(d_cnt, 0, 8));
+        k_check_gmax<<<148 * 8, 256>>>(d_spec, d_gmax, (int64_t)tracks * T, d_cnt);
+        CK(cudaMemcpy(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost));
+        printf("group maxima: %llu of %lld entries differ from the stored rows\n", h_cnt, (long long)tracks * T * 32);
+        cudaFree(d_cnt);
+    }
     // spot check against a double-precision DFT: tolerance |dS| <= AID_SPEC_TOL * max(|S|, 1)
     std::vector<float> pcm(ns), row(AID_NBINS);
     double worst = 0; int bad = 0;
