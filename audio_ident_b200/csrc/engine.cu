@@ -185,6 +185,16 @@ int aid_build_plan_windows(const int64_t* begin_of, const int64_t* end_of, int c
         }
     }
     plan.first_punit[count] = (uint32_t)plan.punits.size();
+    // full-length runs first, the shorter tails of the tracks after them: a launch is a wave or two of warps (148 SMs x
+    // 16-20 resident warps), so the last warps to start should be the short ones. The order of the run list decides only
+    // which warp streams which run -- every run writes its own blocks' slot lists.
+    {
+        const int64_t full_rows = run_blocks * AID_PEAK_BLOCK_FRAMES;
+        std::stable_partition(plan.pruns.begin(), plan.pruns.end(), [&](const aid_peak_run& r) {
+            const aid_peak_unit& u = plan.punits[r.first_unit];
+            return (int64_t)u.n_frames - u.row0 >= full_rows;
+        });
+    }
     plan.total_frames = plan.frame_off[count];
     plan.peak_cap = (int64_t)plan.punits.size() * AID_PEAK_BLOCK_CAP;
     plan.hash_cap = plan.peak_cap * AID_FANOUT;

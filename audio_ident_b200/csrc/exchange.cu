@@ -411,20 +411,60 @@ static int identify_host(aid_engine* e, aid_exchange* x, const float* pcm, const
     Slot& s = e->slot[0];
     Index* ix = e->index;
     const int P = x->world, r = x->rank;
-    const int lo = (int)((int64_t)r * n_windows / P), hi = (int)((int64_t)(r + 1) * n_windows / P);
-    int64_t s0 = INT64_MAX, s1 = INT64_MIN;
-    for (int i = lo; i < hi; i++) { s0 = std::min(s0, win_begin[i]); s1 = std::max(s1, win_end[i]); }
-    const int64_t samples = hi > lo ? s1 - s0 : 0;
-    if (hi <= lo) s0 = 0;
-    if (samples < 0 || (samples > 0 && !pcm)) return AID_E_ARG;
+    // The batch is cut into up to kParts (8) consecutive parts, each a complete step (fingerprint, exchange, vote, merge) on the
+    // engine's stream, and ALL uploads are queued first on a second stream: while part k is computed, part k + 1 crosses
+    // PCIe. A step's compute (7-10 ms for 4,096 queries) then hides behind the copy (24-51 ms) instead of following it.
+    // Every rank cuts the same batch the same way, so the ranks' epochs stay in step; rank r uploads, for every part, only
+    // the samples its slice of that part covers.
+    constexpr int kParts = 8;
+    const int parts = std::max(1, std::min(kParts, n_windows / 64));      // at least 64 windows per part
+    int64_t span0[kParts], span1[kParts];
+    int64_t all0 = INT64_MAX, all1 = INT64_MIN;
+    for (int k = 0; k < parts; k++) {
+        const int w0 = (int)((int64_t)k * n_windows / parts), w1 = (int)((int64_t)(k + 1) * n_windows / parts), nk = w1 - w0;
+        const int lo = w0 + (int)((int64_t)r * nk / P), hi = w0 + (int)((int64_t)(r + 1) * nk / P);
+        int64_t a = INT64_MAX, b = INT64_MIN;
+        for (int i = lo; i < hi; i++) {
+            if (win_end[i] < win_begin[i]) return AID_E_ARG;
+            a = std::min(a, win_begin[i]); b = std::max(b, win_end[i]);
+        }
+        if (hi <= lo) { a = 0; b = 0; }
+        span0[k] = a; span1[k] = b;
+        if (b > a) { all0 = std::min(all0, a); all1 = std::max(all1, b); }
+    }
+    const int64_t samples = all1 > all0 ? all1 - all0 : 0;
+    if (samples == 0) all0 = 0;
+    if (samples > 0 && !pcm) return AID_E_ARG;
     AID_CUDA(e, s.pcm.ensure((size_t)std::max<int64_t>(samples, 1) * sizeof(float)));
     AID_CUDA(e, ix->rows.ensure((size_t)n_windows * max_rows * sizeof(aid_match_row)));
     AID_CUDA(e, ix->rows_n.ensure((size_t)n_windows * 4));
-    if (samples > 0)
-        AID_CUDA(e, cudaMemcpyAsync(s.pcm.p, pcm + s0, (size_t)samples * sizeof(float), cudaMemcpyHostToDevice, s.st));
-    int rc = identify_core(e, x, s.pcm.as<float>(), s0, win_begin, win_end, n_windows, d_track_map, n_map,
-                           ix->rows.as<aid_match_row>(), max_rows, ix->rows_n.as<int32_t>(), s.st);
-    if (rc) return rc;
+    cudaStream_t copy_st = parts > 1 ? e->slot[1].st : s.st;
+    cudaEvent_t landed[kParts] = {};
+    AID_CUDA(e, cudaStreamSynchronize(s.st));          // the PCM buffer may still be read by an earlier call on this engine
+    int rc = AID_OK;
+    // issue order: upload k, then step k (whose small descriptor upload queues behind upload k on the copy engine and in
+    // front of upload k + 1), so step k runs while part k + 1 is on the bus
+    for (int k = 0; k < parts && rc == AID_OK; k++) {
+        const int w0 = (int)((int64_t)k * n_windows / parts), w1 = (int)((int64_t)(k + 1) * n_windows / parts);
+        if (span1[k] > span0[k]) {
+            cudaError_t ce = cudaMemcpyAsync(s.pcm.as<float>() + (span0[k] - all0), pcm + span0[k],
+                                             (size_t)(span1[k] - span0[k]) * sizeof(float), cudaMemcpyHostToDevice, copy_st);
+            if (ce != cudaSuccess) { rc = aid_fail_cuda(e, ce, "cudaMemcpyAsync(query pcm)"); break; }
+        }
+        if (parts > 1) {
+            cudaError_t ce = cudaEventCreateWithFlags(&landed[k], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventRecord(landed[k], copy_st);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s.st, landed[k], 0);
+            if (ce != cudaSuccess) { rc = aid_fail_cuda(e, ce, "cudaEventRecord(query pcm)"); break; }
+        }
+        rc = identify_core(e, x, s.pcm.as<float>(), all0, win_begin + w0, win_end + w0, w1 - w0, d_track_map, n_map,
+                           ix->rows.as<aid_match_row>() + (int64_t)w0 * max_rows, max_rows, ix->rows_n.as<int32_t>() + w0, s.st);
+    }
+    if (parts > 1) {
+        cudaStreamSynchronize(copy_st);
+        for (int k = 0; k < parts; k++) if (landed[k]) cudaEventDestroy(landed[k]);
+    }
+    if (rc) { cudaStreamSynchronize(s.st); return rc; }
     if (rows_count > 0) {
         AID_CUDA(e, cudaMemcpyAsync(rows, ix->rows.as<aid_match_row>() + (int64_t)rows_first * max_rows,
                                     (size_t)rows_count * max_rows * sizeof(aid_match_row), cudaMemcpyDeviceToHost, s.st));

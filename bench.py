@@ -316,36 +316,77 @@ def main():
     ms_per_step = ms_max / args.steps
     value = world * audio_hours / (ms_per_step / 1e3)
 
-    # ---- roofline of the two streaming kernels (algorithmic bytes: SURVEY.md section 8(d))
+    # ---- roofline of the two streaming kernels (algorithmic bytes: SURVEY.md section 8(d), DESIGN.md section 4)
+    # Product configuration (round 2): the STFT kernel also writes the 16-bin group maxima (128 B per frame) and the peak
+    # kernel streams those instead of the 2 KB spectrogram row, so per frame the STFT moves 512 B of PCM in + 2048 B of
+    # spectrogram + 128 B of summary out, and the peak kernel 128 B in (it is latency bound, not HBM bound, now).
     peak, peak_src = measured_peaks()
+    summary = os.environ.get("AID_PEAK_SUMMARY", "1") != "0" and os.environ.get("AID_STFT_VARIANT", "7") != "0"
     total_audio_s = n * args.seconds * args.steps
     total_frames = n * frames * args.steps
-    stft_bytes = n * samples * 4 * args.steps + total_frames * 512 * 4
-    peaks_bytes = total_frames * 512 * 4
+    stft_bytes = n * samples * 4 * args.steps + total_frames * 512 * 4 + (total_frames * 32 * 4 if summary else 0)
+    peaks_bytes = total_frames * 32 * 4 if summary else total_frames * 512 * 4
     kern = {}
-    # DRAM bytes per launch from the committed ncu capture (profiles/traffic_r01.json), scaled to this run's average
-    # launch size; None if the capture is missing
+    # DRAM bytes per launch from the committed ncu capture, scaled to this run's average launch size; None if missing
+    cap_name = "traffic_r02b.json" if summary else "traffic_r02.json"
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", cap_name)))
     except Exception:
         cap = None
     for name, b in (("stft", stft_bytes), ("peaks", peaks_bytes)):
         t_ms, cnt = stage[name]
         ach = b / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0
         traffic = None
-        if cap and cnt:
+        if cap and cnt and ("k_" + name) in cap:
             c = cap["k_" + name]
             traffic = (c["dram_bytes_read"] + c["dram_bytes_write"]) * (total_frames / cnt) / cap["frames_per_launch"]
         kern[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                       "traffic": traffic, "algorithmic_bytes_per_launch": b / max(cnt, 1), "launches": cnt,
                       "avg_launch_ms": t_ms / max(cnt, 1), "share_of_step": t_ms / ms if ms > 0 else None}
+    kern["stft"]["kernel"] = "k_stft_packed (f32x2)" + (" + group maxima" if summary else "")
+    if summary:
+        kern["peaks"]["note"] = ("streams the STFT's group maxima (128 B per frame) instead of the 2 KB row: bound by latency "
+                                 "and instruction issue, not HBM; the row-streaming form is in `ab`")
+        kern["peaks"]["spectrogram_bytes_not_read_per_launch"] = total_frames * 512 * 4 / max(stage["peaks"][1], 1)
     for name in ("compact", "hash"):
         t_ms, cnt = stage[name]
         kern[name] = {"avg_group_ms": t_ms / max(cnt, 1), "share_of_step": t_ms / ms if ms > 0 else None}
     roofline = {k: kern["stft"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
-    roofline["kernel"] = "k_stft"
+    roofline["kernel"] = "k_stft_packed"
     roofline["peak_source"] = peak_src
-    roofline["traffic_source"] = "profiles/traffic_r02.json (ncu --set full), scaled to this run's launch size"
+    roofline["traffic_source"] = f"profiles/{cap_name} (ncu --set full), scaled to this run's launch size"
+
+    # ---- A/B of the kernel generations on the same inputs (two steps each; results are bit-identical, tests/test_gpu_fingerprint.py):
+    # round-1 scalar STFT + row-streaming peaks, packed STFT + row-streaming peaks, and the product configuration above
+    ab = {}
+    if rank == 0 or world > 1:
+        try:
+            for label, variant, summ in (("scalar_stft_rows_peaks", 0, False), ("packed_stft_rows_peaks", 7, False)):
+                eng.set_kernels(variant, summ)
+                step_device()
+                barrier()
+                eng.stage_times()
+                eng.set_stage_timing(True)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(2):
+                    step_device()
+                a1.record()
+                barrier()
+                st2 = eng.stage_times()
+                eng.set_stage_timing(False)
+                b_stft = (n * samples * 4 + n * frames * 512 * 4) * 2
+                b_peaks = n * frames * 512 * 4 * 2
+                ab[label] = {"ms_per_step": a0.elapsed_time(a1) / 2,
+                             "stft_ms_per_launch": st2["stft"][0] / max(st2["stft"][1], 1),
+                             "stft_frac": b_stft / (st2["stft"][0] / 1e3) / 1e9 / peak if st2["stft"][0] > 0 else None,
+                             "peaks_ms_per_launch": st2["peaks"][0] / max(st2["peaks"][1], 1),
+                             "peaks_frac": b_peaks / (st2["peaks"][0] / 1e3) / 1e9 / peak if st2["peaks"][0] > 0 else None}
+        except Exception as ex:
+            log(f"[bench] kernel A/B leg failed: {ex!r}")
+        finally:
+            eng.set_kernels(int(os.environ.get("AID_STFT_VARIANT", "7")), summary)
+    kern["ab"] = ab
 
     # ---- end to end through the host-buffer C ABI call
     e2e = None

@@ -237,3 +237,50 @@ def test_fused_exchange_single_rank_and_timeout(engine):
     assert (nrows.cpu().numpy() == -1).all()
     x2.close(); peer.close()
     engine.index_clear()
+
+
+def test_host_entry_pipelines_its_uploads_and_keeps_the_rows(engine):
+    """aid_identify_exchange_host / _windows_host cut a batch of >= 128 windows into up to eight parts whose uploads overlap the
+    previous part's step (csrc/exchange.cu identify_host): rows and counts must equal the device-resident single step,
+    for separate windows and for overlapping windows of shared clips, also when only a slice of the rows is returned."""
+    torch = pytest.importorskip("torch")
+    tracks = [synth.make_track(1200 + k, 12.0) for k in range(12)]
+    engine.index_clear()
+    pcm, off = ragged(tracks)
+    sh = sharded.ShardedIdentifier(engine, 0, 1, device=torch.device("cuda", 0))
+    assert sh.add(pcm, off, list(range(len(tracks)))).all()
+    engine.index_commit()
+    sh.enable_peer_exchange(512, connect=True)
+    try:
+        clips = [synth.make_query(tracks[q % 12], 500 + q, 5.0, 20.0)[0] for q in range(101)]
+        wins = []
+        for c in clips:
+            wins += [c[:56000], c[12000:68000], c[24000:]]
+        wins[7] = np.zeros(300, np.float32)                                   # no fingerprints
+        qp, qo = ragged(wins)
+        n = len(wins)
+        assert n >= 256
+        d_pcm = torch.from_numpy(qp).cuda()
+        ref, ref_n = sh.query(d_pcm.data_ptr(), qo, device=True)
+        ref, ref_n = ref.cpu().numpy(), ref_n.cpu().numpy()
+        rows, nr = sh.query_host(qp, qo)
+        assert np.array_equal(nr, ref_n)
+        for q in range(n):
+            got = np.stack([rows[q, :nr[q]][f] for f in rows.dtype.names], axis=1).astype(np.int64) if nr[q] else np.zeros((0, 5), np.int64)
+            assert np.array_equal(got, ref[q, :nr[q]]), q
+        rows2, nr2 = sh.query_host(qp, qo, rows_first=100, rows_count=57)
+        assert np.array_equal(nr2, ref_n[100:157])
+        # the same windows as offsets into ONE upload of every clip
+        cp, co = ragged(clips)
+        begin = np.concatenate([[co[i], co[i] + 12000, co[i] + 24000] for i in range(len(clips))]).astype(np.int64)
+        end = np.concatenate([[co[i] + 56000, co[i] + 68000, co[i + 1]] for i in range(len(clips))]).astype(np.int64)
+        rows3, nr3 = sh.query_host(cp, (begin, end))
+        keep = np.arange(n) != 7                                              # window 7 was replaced by silence above
+        assert np.array_equal(nr3[keep], ref_n[keep])
+        for q in np.flatnonzero(keep):
+            got = np.stack([rows3[q, :nr3[q]][f] for f in rows3.dtype.names], axis=1).astype(np.int64)
+            assert np.array_equal(got, ref[q, :nr3[q]]), q
+    finally:
+        if sh._xchg is not None:
+            sh._xchg.close()
+        engine.index_clear()
