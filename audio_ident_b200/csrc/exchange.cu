@@ -414,10 +414,11 @@ static int identify_host(aid_engine* e, aid_exchange* x, const float* pcm, const
     // The batch is cut into up to kParts (8) consecutive parts, each a complete step (fingerprint, exchange, vote, merge) on the
     // engine's stream, and ALL uploads are queued first on a second stream: while part k is computed, part k + 1 crosses
     // PCIe. A step's compute (7-10 ms for 4,096 queries) then hides behind the copy (24-51 ms) instead of following it.
-    // Every rank cuts the same batch the same way, so the ranks' epochs stay in step; rank r uploads, for every part, only
-    // the samples its slice of that part covers.
     constexpr int kParts = 8;
-    const int parts = std::max(1, std::min(kParts, n_windows / 64));      // at least 64 windows per part
+    // Only on a single rank: with P ranks the contract is that rank r is handed, and uploads, exactly the samples of ITS slice
+    // [r n / P, (r + 1) n / P) of the batch (a caller may pass a pointer that is valid for that slice only), and a part of
+    // the batch would give it other windows.
+    const int parts = P == 1 ? std::max(1, std::min(kParts, n_windows / 64)) : 1;      // at least 64 windows per part
     int64_t span0[kParts], span1[kParts];
     int64_t all0 = INT64_MAX, all1 = INT64_MIN;
     for (int k = 0; k < parts; k++) {
