@@ -538,7 +538,12 @@ def main():
                        "frames_per_track": frames, "sub_batch_tracks": args.sub_batch,
                        "l2_policy": f"inputs larger than L2: {n * samples * 4 / 1e9:.1f} GB PCM + "
                                     f"{min(args.sub_batch, n) * frames * 2048 / 1e9:.1f} GB spectrogram per launch group",
-                       "parallelism": f"tracks sharded over {world} rank(s), no collective"},
+                       "parallelism": f"tracks sharded over {world} rank(s), no collective",
+                       "pipeline": ("spectrogram materialised once (written by the STFT kernel, read back only around surviving "
+                                    "peak candidates); the peak kernel streams the STFT's 16-bin group maxima: 352,000 B of "
+                                    "algorithmic HBM traffic per audio-second (SURVEY 8(d): 576,300 B with the spectrogram read "
+                                    "back, 64,000 B fully fused)") if summary else
+                                   "spectrogram materialised once and read back by the peak kernel (576,300 B per audio-second)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kern,
             "cpu_baseline": cpu, "parity_sample": parity,
             "per_gpu_value": value / world,
