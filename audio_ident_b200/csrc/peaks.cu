@@ -27,6 +27,11 @@
 //  * Peaks collect in a small per-warp buffer and are put in (t, f) order by a warp bitonic network.
 // Every comparison is <= against the candidate's own value, so exact ties behave as the specification says.
 // HBM traffic: every spectrogram row is read once per block (+24/256 halo rows, L2 hits); peaks out are noise.
+// Two forms of the row pass (template parameter SUMMARY of k_peaks), identical peaks:
+//  * rows:    the warp streams the spectrogram rows themselves (2 KB per row; HBM bound, 0.91-0.94 of the roofline);
+//  * summary: the STFT kernel has already reduced every row to its 32 group maxima (stft.cu GroupMax) and the warp streams
+//             those 128 B per row through a cp.async ring; the spectrogram is read only around surviving candidates
+//             (the product path; bound by instruction issue and latency; profiles/r02_peaks_summary.md).
 #include "common.cuh"
 
 namespace {

@@ -17,9 +17,12 @@
 //    per frame: PCM goes global -> registers with fully coalesced 128 B warp loads and every sample is
 //    read from HBM once per unit (8x frame overlap is served from the register ring, never re-read).
 //  * Rows of the spectrogram (512 floats = 2 KB) are written with 128 B coalesced warp stores.
-// The kernel is FP32-issue-bound, not HBM-bound (about 1.1 k FP32 instructions per lane per frame pair);
-// packed FFMA2/FADD2 were measured to issue at half rate on sm_100a (tools/microbench/fp32_issue.cu), so the
-// butterflies stay scalar.
+// Two kernels with bit-identical output:
+//  * k_stft        (round 1) scalar FP32 butterflies; issue bound (1,326 instructions per frame pair, 1,060 of them FP32);
+//                  kept as the reference point of the A/B leg in bench.py and of tests/test_gpu_fingerprint.py.
+//  * k_stft_packed (round 2, the product kernel) the same operations as two-lane f32x2 instructions (FFMA2 / FADD2 / FMUL2):
+//                  897 instructions per frame pair, bound by the FP32 pipe itself; optionally also writes the maxima of
+//                  every row's 16-bin groups for the peak kernel. Measurements: profiles/r02_stft_packed.md.
 #include "common.cuh"
 #include <stdlib.h>
 
