@@ -284,3 +284,34 @@ def test_host_entry_pipelines_its_uploads_and_keeps_the_rows(engine):
         if sh._xchg is not None:
             sh._xchg.close()
         engine.index_clear()
+
+
+def test_host_entry_error_in_a_later_part_leaves_the_engine_usable(engine):
+    """A window longer than a vote window may be (AID_E_TOO_LONG) that sits in a later part of a pipelined batch: the call
+    fails as a whole, nothing hangs, and the next call on the same exchange works."""
+    torch = pytest.importorskip("torch")
+    from audio_ident_b200.engine import EngineError
+    tracks = [synth.make_track(1300 + k, 8.0) for k in range(4)]
+    engine.index_clear()
+    pcm, off = ragged(tracks)
+    sh = sharded.ShardedIdentifier(engine, 0, 1, device=torch.device("cuda", 0))
+    assert sh.add(pcm, off, list(range(len(tracks)))).all()
+    engine.index_commit()
+    sh.enable_peer_exchange(512, connect=True)
+    try:
+        wins = [tracks[k % 4][1000 * (k % 7):1000 * (k % 7) + 56000] for k in range(200)]
+        good, good_off = ragged(wins)
+        rows_ok, n_ok = sh.query_host(good, good_off)
+        assert (n_ok >= 1).all()
+        bad = list(wins)
+        bad[150] = np.zeros(270 * 16000, np.float32)                          # 33,742 frames > AID_QUERY_MAX_FRAMES
+        bp, bo = ragged(bad)
+        with pytest.raises(EngineError) as ei:
+            sh.query_host(bp, bo)
+        assert ei.value.status == -4                                          # AID_E_TOO_LONG
+        rows2, n2 = sh.query_host(good, good_off)
+        assert np.array_equal(n2, n_ok)
+    finally:
+        if sh._xchg is not None:
+            sh._xchg.close()
+        engine.index_clear()
