@@ -344,6 +344,11 @@ def main():
                       "traffic": traffic, "algorithmic_bytes_per_launch": b / max(cnt, 1), "launches": cnt,
                       "avg_launch_ms": t_ms / max(cnt, 1), "share_of_step": t_ms / ms if ms > 0 else None}
     kern["stft"]["kernel"] = "k_stft_packed (f32x2)" + (" + group maxima" if summary else "")
+    kern["stft"]["algorithmic_bytes_per_frame"] = 512 + 2048 + (128 if summary else 0)
+    # the same launch time against SURVEY 8(d)'s original numerator (PCM in + spectrogram out only), for comparison across rounds
+    t_ms, cnt = stage["stft"]
+    b8d = n * samples * 4 * args.steps + total_frames * 512 * 4
+    kern["stft"]["frac_on_survey_8d_bytes"] = (b8d / (t_ms / 1e3) / 1e9 / peak) if t_ms > 0 else None
     if summary:
         kern["peaks"]["note"] = ("streams the STFT's group maxima (128 B per frame) instead of the 2 KB row: bound by latency "
                                  "and instruction issue, not HBM; the row-streaming form is in `ab`")
@@ -353,6 +358,8 @@ def main():
         kern[name] = {"avg_group_ms": t_ms / max(cnt, 1), "share_of_step": t_ms / ms if ms > 0 else None}
     roofline = {k: kern["stft"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = "k_stft_packed"
+    roofline["algorithmic_bytes_per_frame"] = kern["stft"]["algorithmic_bytes_per_frame"]
+    roofline["frac_on_survey_8d_bytes"] = kern["stft"]["frac_on_survey_8d_bytes"]
     roofline["peak_source"] = peak_src
     roofline["traffic_source"] = f"profiles/{cap_name} (ncu --set full), scaled to this run's launch size"
 
