@@ -42,6 +42,22 @@ def test_deterministic_and_independent_of_batching(engine, corpus):
         assert np.array_equal(x, y)
 
 
+def test_kernel_generations_agree_on_3000_tracks(engine, corpus):
+    """The round-1 kernels (scalar STFT, row-streaming peaks), the packed STFT with row-streaming peaks and the product
+    configuration (packed STFT + group maxima for the peak kernel) must emit the same hashes, anchors and offsets for
+    every one of 3,000 tracks (csrc/stft.cu, csrc/peaks.cu; aid_engine_set_kernels)."""
+    try:
+        engine.set_kernels(0, False)
+        ref = fingerprint_all(engine, corpus, 1000)
+        for variant, summary in ((7, False), (7, True)):
+            engine.set_kernels(variant, summary)
+            got = fingerprint_all(engine, corpus, 750)
+            for x, y in zip(ref, got):
+                assert np.array_equal(x, y), (variant, summary)
+    finally:
+        engine.set_kernels(7, True)
+
+
 def test_every_hash_obeys_the_specification(engine, corpus):
     h, t, off = fingerprint_all(engine, corpus, 1500)
     f1, f2, dt = (h >> 15).astype(np.int64), ((h >> 6) & 511).astype(np.int64), (h & 63).astype(np.int64)
