@@ -92,11 +92,11 @@ inline void aid_fill_stft_tables(float* window, float* twist) {
     }
 }
 
-// variant: 0 = scalar FP32 kernel (round 1), 7 = packed f32x2 kernel, software-pipelined, with L1 prefetch (default; other
-// values are A/B shapes, see stft.cu). d_gmax (nullable, packed variants only): [rows][32] group maxima for the peak kernel.
+// variant: 0 = scalar FP32 kernel (round 1), 5 = packed f32x2 kernel with L1 prefetch (default), 7 = the same with the
+// separation software-pipelined into the next trip (other values are A/B shapes, see stft.cu). d_gmax (nullable, packed variants only): [rows][32] group maxima for the peak kernel.
 cudaError_t aid_launch_stft_variant(int variant, const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
                                     int n_units, float* d_spec, float* d_gmax, cudaStream_t st);
-int aid_stft_default_variant();      // 7, or the environment's AID_STFT_VARIANT (measurement runs)
+int aid_stft_default_variant();      // 5, or the environment's AID_STFT_VARIANT (measurement runs)
 
 // d_gmax (nullable): the STFT's group maxima; with it the peak kernel streams 128 B per row instead of the 2 KB row
 cudaError_t aid_launch_peaks(const float* d_spec, const float* d_gmax, const aid_peak_unit* d_units, const aid_peak_run* d_runs,

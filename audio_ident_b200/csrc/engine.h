@@ -80,7 +80,7 @@ struct aid_engine {
     aid_tables tables{};
     Index* index = nullptr;
     // kernel selection (aid_engine_set_kernels; the defaults are the product path, the others exist for tests and A/B runs)
-    int stft_variant = 7;        // stft.cu aid_launch_stft_variant: 0 = scalar FP32 kernel, 7 = packed f32x2 kernel
+    int stft_variant = 5;        // stft.cu aid_launch_stft_variant: 0 = scalar FP32 kernel, 5 = packed f32x2 kernel (7: + pipelined separation)
     bool peak_summary = true;    // the STFT also writes the 16-bin group maxima and the peak kernel streams those
     // optional per-stage timing (aid_engine_set_stage_timing)
     bool timing = false;

@@ -751,6 +751,6 @@ cudaError_t aid_launch_stft_variant(int variant, const aid_tables& tb, const flo
 }
 
 int aid_stft_default_variant() {
-    static const int variant = [] { const char* v = getenv("AID_STFT_VARIANT"); return v ? atoi(v) : 7; }();
+    static const int variant = [] { const char* v = getenv("AID_STFT_VARIANT"); return v ? atoi(v) : 5; }();
     return variant;
 }

@@ -99,9 +99,9 @@ class Engine:
     def set_stage_timing(self, on: bool) -> None:
         self._check(self._L.aid_engine_set_stage_timing(self._h, int(bool(on))))
 
-    def set_kernels(self, stft_variant: int = 7, peak_summary: bool = True) -> None:
+    def set_kernels(self, stft_variant: int = 5, peak_summary: bool = True) -> None:
         """Kernel selection for tests and A/B runs (include/audio_ident_b200.h aid_engine_set_kernels): 0 = the scalar
-        FP32 STFT kernel, 7 = the packed one (default); peak_summary = the peak kernel streams the STFT's group maxima.
+        FP32 STFT kernel, 5 = the packed one (default; 7 adds the software-pipelined separation); peak_summary = the peak kernel streams the STFT's group maxima.
         Results are bit-identical for every choice."""
         self._check(self._L.aid_engine_set_kernels(self._h, int(stft_variant), int(bool(peak_summary))))
 

@@ -321,7 +321,7 @@ def main():
     # kernel streams those instead of the 2 KB spectrogram row, so per frame the STFT moves 512 B of PCM in + 2048 B of
     # spectrogram + 128 B of summary out, and the peak kernel 128 B in (it is latency bound, not HBM bound, now).
     peak, peak_src = measured_peaks()
-    summary = os.environ.get("AID_PEAK_SUMMARY", "1") != "0" and os.environ.get("AID_STFT_VARIANT", "7") != "0"
+    summary = os.environ.get("AID_PEAK_SUMMARY", "1") != "0" and os.environ.get("AID_STFT_VARIANT", "5") != "0"
     total_audio_s = n * args.seconds * args.steps
     total_frames = n * frames * args.steps
     stft_bytes = n * samples * 4 * args.steps + total_frames * 512 * 4 + (total_frames * 32 * 4 if summary else 0)
@@ -368,7 +368,7 @@ def main():
     ab = {}
     if rank == 0 or world > 1:
         try:
-            for label, variant, summ in (("scalar_stft_rows_peaks", 0, False), ("packed_stft_rows_peaks", 7, False)):
+            for label, variant, summ in (("scalar_stft_rows_peaks", 0, False), ("packed_stft_rows_peaks", 5, False)):
                 eng.set_kernels(variant, summ)
                 step_device()
                 barrier()
@@ -392,7 +392,7 @@ def main():
         except Exception as ex:
             log(f"[bench] kernel A/B leg failed: {ex!r}")
         finally:
-            eng.set_kernels(int(os.environ.get("AID_STFT_VARIANT", "7")), summary)
+            eng.set_kernels(int(os.environ.get("AID_STFT_VARIANT", "5")), summary)
     kern["ab"] = ab
 
     # ---- end to end through the host-buffer C ABI call

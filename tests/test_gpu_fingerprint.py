@@ -223,13 +223,13 @@ def test_packed_stft_kernel_is_bit_identical_to_the_scalar_one(engine):
     try:
         engine.set_kernels(0, False)
         ref = engine.stft(pcm, off)
-        for variant in (7, 5, 3, 1, 15):
+        for variant in (5, 7, 3, 1, 13):
             engine.set_kernels(variant, False)
             got = engine.stft(pcm, off)
             assert ref.shape == got.shape
             assert np.array_equal(ref.view(np.uint32), got.view(np.uint32)), f"variant {variant}"
     finally:
-        engine.set_kernels(7, True)
+        engine.set_kernels(5, True)
 
 
 def test_peak_summary_path_gives_the_same_fingerprints(engine):
@@ -240,19 +240,19 @@ def test_peak_summary_path_gives_the_same_fingerprints(engine):
     try:
         engine.set_kernels(0, False)
         ref = engine.fingerprint(pcm, off)
-        for variant, summary in ((7, False), (7, True), (5, True)):
+        for variant, summary in ((5, False), (5, True), (7, True)):
             engine.set_kernels(variant, summary)
             got = engine.fingerprint(pcm, off)
             for x, y in zip(ref, got):
                 assert np.array_equal(x, y), (variant, summary)
-        engine.set_kernels(7, True)
+        engine.set_kernels(5, True)
         engine.set_max_batch_frames(700)
         got = engine.fingerprint(pcm, off)
         for x, y in zip(ref, got):
             assert np.array_equal(x, y)
     finally:
         engine.set_max_batch_frames(8 * 1024 * 1024)
-        engine.set_kernels(7, True)
+        engine.set_kernels(5, True)
 
 
 def test_peak_summary_path_with_exact_ties(engine, oracle):
@@ -262,11 +262,11 @@ def test_peak_summary_path_with_exact_ties(engine, oracle):
     x[16000:48000] = 0.0                                   # silence: S = 0 everywhere, below the gate
     x[64000:96000] = x[32000 + 64000:64000 + 64000]
     try:
-        engine.set_kernels(7, True)
+        engine.set_kernels(5, True)
         h1 = engine.fingerprint(x, [0, len(x)])
         S = engine.stft(x, [0, len(x)])
         pk, _, _ = engine.peaks(S, [0, S.shape[0]])       # row-streaming peak kernel on the same spectrogram
         rh, rt = oracle.hashes(pk)
         assert np.array_equal(h1[0], rh) and np.array_equal(h1[1], rt)
     finally:
-        engine.set_kernels(7, True)
+        engine.set_kernels(5, True)
