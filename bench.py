@@ -77,6 +77,16 @@ class ClockSampler:
         self.gpu = gpu
         self.proc = None
         self.path = None
+        self.offset = 0
+
+    def mark(self):
+        """Start of the timed region: samples before this point (the sampler is started ahead of the warm-up steps, because
+        nvidia-smi needs a few hundred ms to come up and a short timed region would otherwise get no sample) are only used
+        if the region itself yields none -- they see the same workload."""
+        try:
+            self.offset = os.path.getsize(self.path) if self.path else 0
+        except OSError:
+            self.offset = 0
 
     def start(self):
         try:
@@ -99,7 +109,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         try:
-            for line in open(self.path):
+            data = open(self.path).read()
+            inside = data[self.offset:]
+            inside = inside[inside.find("\n") + 1:] if self.offset and not data[:self.offset].endswith("\n") else inside
+            lines = [ln for ln in inside.splitlines() if ln.count(",") >= 6]
+            if not lines:
+                lines = [ln for ln in data.splitlines() if ln.count(",") >= 6][-5:]
+            for line in lines:
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 7:
                     continue
@@ -290,14 +306,15 @@ def main():
         for k0, off in groups:
             eng.fingerprint_dev(d_pcm.data_ptr() + k0 * samples * 4, off, stream)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
     eng.stage_times()
     eng.set_stage_timing(True)
     launches0 = eng.launches
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
