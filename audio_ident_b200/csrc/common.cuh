@@ -93,7 +93,7 @@ inline void aid_fill_stft_tables(float* window, float* twist) {
 }
 
 // variant: 0 = scalar FP32 kernel (round 1), 5 = packed f32x2 kernel with L1 prefetch (default), 7 = the same with the
-// separation software-pipelined into the next trip (other values are A/B shapes, see stft.cu). d_gmax (nullable, packed variants only): [rows][32] group maxima for the peak kernel.
+// separation software-pipelined into the next trip, 16 = the warp-specialised form (other values are A/B shapes, see stft.cu). d_gmax (nullable, packed variants only): [rows][32] group maxima for the peak kernel.
 cudaError_t aid_launch_stft_variant(int variant, const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units,
                                     int n_units, float* d_spec, float* d_gmax, cudaStream_t st);
 int aid_stft_default_variant();      // 5, or the environment's AID_STFT_VARIANT (measurement runs)

@@ -236,7 +236,7 @@ int aid_slot_prepare(aid_engine* e, Slot& s, const Plan& plan, bool need_pcm, in
 }
 
 extern "C" int aid_engine_set_kernels(aid_engine* e, int stft_variant, int peak_summary) {
-    if (!e || stft_variant < 0 || stft_variant > 15) return AID_E_ARG;
+    if (!e || stft_variant < 0 || stft_variant > 31) return AID_E_ARG;
     e->stft_variant = stft_variant;
     e->peak_summary = peak_summary != 0;
     return AID_OK;

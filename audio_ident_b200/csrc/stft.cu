@@ -697,6 +697,135 @@ k_stft_packed(const float* __restrict__ twist, const float* __restrict__ pcm, co
 
 }  // namespace
 
+// =====================================================================================================
+// Warp-specialised form of the packed kernel (variant bit 4): a PRODUCER warp runs the first transform of a unit (sample
+// ring, window stage, stages 1-4, STS of the transposed tile) and a CONSUMER warp the second (gather + stage 0, stages
+// 1-4, separation, log, stores, group maxima); the two hand tiles over through two shared-memory buffers guarded by
+// mbarriers (full / empty, 32 arrivals each: every lane releases its own stores / loads). Neither role holds the other's
+// state, so the kernel fits 128 registers and an SM holds 2 CTAs x 8 warps = 16 warps instead of 12: the question it
+// answers is whether the packed kernel's missing overlap of its shared-memory phases with arithmetic (profiles/
+// r02_stft_packed.md section 4) is a matter of resident warps. Same operations on every element: bit-identical output.
+constexpr int kWsPairs = 4;                                   // (producer, consumer) pairs = units per CTA
+constexpr int kWsSmem = kWsPairs * 2 * kTileFloats * 8 + 32 * kTabStride * 4 + 32 * kPTwistStride * 4 + kWsPairs * 4 * 8;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{ .reg .pred p;\n"
+                 "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra W;\n}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+template <bool SUM>
+__global__ void __launch_bounds__(kWsPairs * 64, 2)
+k_stft_ws(const float* __restrict__ twist, const float* __restrict__ pcm, const aid_stft_unit* __restrict__ units, int n_units,
+          float* __restrict__ spec, float* __restrict__ gmax) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 (*s_tile)[kTileFloats] = reinterpret_cast<float2 (*)[kTileFloats]>(smem_raw);      // [pair * 2 + buffer]
+    float* s_win = reinterpret_cast<float*>(s_tile + kWsPairs * 2);
+    float* s_twist = s_win + 32 * kTabStride;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_twist + 32 * kPTwistStride);   // [pair][full0, full1, empty0, empty1]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp >> 1;
+    const bool producer = (warp & 1) == 0;
+    {
+        const float4* src = reinterpret_cast<const float4*>(twist + AID_TWIST_IMAGE);
+        float4* dst = reinterpret_cast<float4*>(s_win);
+        for (int i = threadIdx.x; i < AID_TWIST_IMAGE_FLOATS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (threadIdx.x < kWsPairs * 4) mbar_init((uint32_t)__cvta_generic_to_shared(s_bar + threadIdx.x), 32);
+    }
+    __syncthreads();
+
+    const int unit_id = blockIdx.x * kWsPairs + pair;
+    if (unit_id >= n_units) return;
+    const aid_stft_unit u = units[unit_id];
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar + pair * 4);               // full[b] = bar0 + 8 b, empty[b] = bar0 + 16 + 8 b
+    float2* tile0 = s_tile[pair * 2];
+
+    if (producer) {
+        const ulonglong2* win2 = reinterpret_cast<const ulonglong2*>(s_win + lane * kTabStride);
+        const int64_t first = (int64_t)u.frame0 * AID_HOP + lane;
+        const float* xp = pcm + u.pcm_begin + first;
+        int rem = (int)(u.n_samples - first);
+        f2 ring[18];
+#pragma unroll
+        for (int j = 0; j < 18; j++)
+            ring[j] = pk(64 * j < rem ? __ldg(xp + 64 * j) : 0.0f, 64 * j + 32 < rem ? __ldg(xp + 64 * j + 32) : 0.0f);
+        int trip = 0;
+        for (int p = 0; p < u.n_frames; p += 2, trip++) {
+            xp += 2 * AID_HOP;
+            rem -= 2 * AID_HOP;
+            if (lane < 9 && 32 * (36 + lane) - lane + 2 * AID_HOP < rem + 2 * AID_HOP)      // lines the loads of the NEXT trip's end will read
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(xp - lane + 2 * AID_HOP + 32 * (36 + lane) - 2 * AID_HOP));
+            f2 nre[16], nim[16], zre[16], zim[16];
+            GroupMax gm;
+            window_and_separate<false, false, 0>(nre, nim, ring, win2, zre, zim, lane, 0, nullptr, nullptr, false, false, gm);
+            pstage<1, 0>(nre, nim); pstage<2, 0>(nre, nim); pstage<3, 0>(nre, nim);
+            const int b = trip & 1, use = trip >> 1;
+            if (use > 0) mbar_wait(bar0 + 16 + 8 * b, (uint32_t)((use - 1) & 1));             // the consumer has read this buffer's previous tile
+            last_stage_store<0>(nre, nim, tile0 + b * kTileFloats + lane);
+            mbar_arrive(bar0 + 8 * b);
+#pragma unroll
+            for (int j = 0; j < 14; j++) ring[j] = ring[j + 4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                ring[14 + j] = pk(64 * (14 + j) < rem ? __ldg(xp + 64 * (14 + j)) : 0.0f,
+                                  64 * (14 + j) + 32 < rem ? __ldg(xp + 64 * (14 + j) + 32) : 0.0f);
+        }
+    } else {
+        const ulonglong2* tw2 = reinterpret_cast<const ulonglong2*>(s_twist + lane * kPTwistStride);
+        const int partner = (32 - lane) & 31;
+        float* row_a = spec + u.spec_row * AID_NBINS + lane;
+        float* gmax_row = SUM ? gmax + u.spec_row * 32 : nullptr;
+        const float c0 = s_twist[lane * kPTwistStride + 32], s0 = s_twist[lane * kPTwistStride + 33];
+        int trip = 0;
+        for (int p = 0; p < u.n_frames; p += 2, trip++) {
+            const int b = trip & 1, use = trip >> 1;
+            const float4* tile_row = reinterpret_cast<const float4*>(tile0 + b * kTileFloats + lane * kTileStride);
+            f2 re[16], im[16];
+            mbar_wait(bar0 + 8 * b, (uint32_t)(use & 1));
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 za = tile_row[q], zb = tile_row[q + 8];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const float ar = r ? za.z : za.x, ai = r ? za.w : za.y, br = r ? zb.z : zb.x, bi = r ? zb.w : zb.y;
+                    const float xr = fmaf(bi, s0, fmaf(br, c0, ar));
+                    const float xi = fmaf(-br, s0, fmaf(bi, c0, ai));
+                    const int e = bitrev5(2 * q + r);
+                    re[e >> 1] = pk(xr, fmaf(2.0f, ar, -xr));
+                    im[e >> 1] = pk(xi, fmaf(2.0f, ai, -xi));
+                }
+            }
+            mbar_arrive(bar0 + 16 + 8 * b);
+            {
+                const ulonglong2 t1 = tw2[0];
+                tpgroups<1, 0, 0>(re, im, t1.x, t1.y);
+                const ulonglong2 t2 = tw2[1];
+                tpgroups<2, 0, 0>(re, im, t2.x, t2.y);
+                const ulonglong2 t3a = tw2[2], t3b = tw2[3];
+                tpgroups<3, 0, 0>(re, im, t3a.x, t3a.y);
+                tpgroups<3, 1, 0>(re, im, t3b.x, t3b.y);
+                const ulonglong2 t4a = tw2[4], t4b = tw2[5];
+                tpgroups<4, 0, 0>(re, im, t4a.x, t4a.y);
+                tpgroups<4, 1, 0>(re, im, t4b.x, t4b.y);
+                const ulonglong2 t4c = tw2[6], t4d = tw2[7];
+                tpgroups<4, 2, 0>(re, im, t4c.x, t4c.y);
+                tpgroups<4, 3, 0>(re, im, t4d.x, t4d.y);
+            }
+            GroupMax gm;
+            separate_all<SUM, 0>(re, im, lane, partner, row_a, gmax_row, true, p + 1 < u.n_frames, gm);
+            row_a += 2 * AID_NBINS;
+            if constexpr (SUM) gmax_row += 64;
+        }
+    }
+}
+
 template <bool PF, bool PIPE, bool SUM>
 static cudaError_t launch_packed(int grid, const aid_tables& tb, const float* d_pcm, const aid_stft_unit* d_units, int n_units,
                                  float* d_spec, float* d_gmax, cudaStream_t st) {
@@ -741,6 +870,19 @@ cudaError_t aid_launch_stft_variant(int variant, const aid_tables& tb, const flo
             resident = sms * AID_STFT_MIN_CTAS;
         }
         if (grid > resident) grid = resident;
+    }
+    if (variant & 16) {                     // warp-specialised form (A/B): 4 units per CTA of 8 warps
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t ce = cudaFuncSetAttribute(k_stft_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem);
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_stft_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmem);
+            if (ce != cudaSuccess) return ce;
+            configured = true;
+        }
+        const int g = (n_units + kWsPairs - 1) / kWsPairs;
+        if (d_gmax) k_stft_ws<true><<<g, kWsPairs * 64, kWsSmem, st>>>(tb.twist, d_pcm, d_units, n_units, d_spec, d_gmax);
+        else k_stft_ws<false><<<g, kWsPairs * 64, kWsSmem, st>>>(tb.twist, d_pcm, d_units, n_units, d_spec, nullptr);
+        return cudaGetLastError();
     }
     const bool pipe = variant & 2, pf = variant & 4;
 #define AID_P(PF, PIPE) (d_gmax ? launch_packed<PF, PIPE, true>(grid, tb, d_pcm, d_units, n_units, d_spec, d_gmax, st) \

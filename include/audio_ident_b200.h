@@ -84,7 +84,7 @@ int         aid_engine_set_stage_timing(aid_engine* e, int on);
 int         aid_engine_stage_times(aid_engine* e, double* ms, int64_t* launches);
 /* Kernel selection for tests and A/B measurements (results are bit-identical for every choice; the defaults are the
  * product path). stft_variant: 0 = the scalar FP32 STFT kernel of round 1, 5 = the packed (f32x2) kernel (default;
- * 7 = the same with the separation software-pipelined into the next trip: faster without the group maxima, slower with them).
+ * 7 = the same with the separation software-pipelined into the next trip: faster without the group maxima, slower with them; 16 = producer / consumer warps, measured slower).
  * peak_summary != 0 (default): the STFT kernel also emits the maxima of the 32 aligned 16-bin groups of every row
  * and the peak kernel streams those 128 B per row instead of re-reading the 2 KB spectrogram row (packed kernel only). */
 int         aid_engine_set_kernels(aid_engine* e, int stft_variant, int peak_summary);
