@@ -1,13 +1,16 @@
-// hasher.cu -- warp-cooperative landmark pairing: sorted peaks -> (hash, t_anchor), sm_100a.
+// hasher.cu -- landmark pairing: sorted peaks -> (hash, t_anchor), sm_100a.
 //
 // Replaces stage a6 of SURVEY.md section 8(a) (fingerprint construction inside the external `olaf_c`,
 // reference audio-ident-service/app/audio/fingerprint.py:117-125). Definition of the result:
 // oracle/aid_oracle.c aid_oracle_hashes(); bit-exact, same order.
 //
-// One warp per anchor: the 32 lanes test the next 32 peaks of the same track in (t, f) order, a ballot
-// ranks the qualifying targets, and the first AID_FANOUT are kept. The pass runs twice: once to count
-// (so that a device-wide scan can give every anchor its dense output position) and once to write.
-// Bytes are negligible next to the spectrogram; this kernel is latency/launch bound.
+// One THREAD per anchor (round 2, second half; round 1 gave a warp to every anchor): the lane walks the peaks that follow
+// its anchor in (t, f) order until it holds AID_FANOUT targets or the time window is over -- a handful of steps, since a
+// window of AID_DT_MAX frames holds few peaks -- and consecutive lanes read consecutive peaks, so the loads coalesce.
+// The warp-per-anchor form spent its time on a chain of four dependent loads per anchor (peak, track, track end, 32
+// candidates) for a ballot that usually found fewer than eight: 0.145 ms per pass and 2048 tracks against 0.02 ms now.
+// The pass runs twice: once to count (so that a device-wide scan can give every anchor its dense output position) and
+// once to write. Bytes are negligible next to the spectrogram.
 #include "common.cuh"
 
 namespace {
@@ -21,39 +24,31 @@ k_hash(const uint32_t* __restrict__ peaks, const uint32_t* __restrict__ peak_tra
        uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pos,
        uint32_t* __restrict__ hash, uint32_t* __restrict__ t_anchor, int64_t hash_cap,
        int32_t* __restrict__ overflow) {
-    const int lane = threadIdx.x & 31;
     const uint32_t n_total = *n_peaks_total;
-    const uint32_t warps = gridDim.x * (kThreads / 32);
+    const uint32_t threads = gridDim.x * kThreads;
     if (!kWrite && blockIdx.x == 0 && threadIdx.x == 0) cnt[n_total] = 0;   // the scan runs over n_total + 1 values
-    for (uint32_t a = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); a < n_total; a += warps) {
+    for (uint32_t a = blockIdx.x * kThreads + threadIdx.x; a < n_total; a += threads) {
         const uint32_t ka = peaks[a];
         const uint32_t end = peak_off[peak_track[a] + 1];
         const int t1 = (int)(ka >> AID_PEAK_F_BITS), f1 = (int)(ka & (AID_NBINS - 1));
-        const uint32_t out0 = kWrite ? pos[a] : 0;
+        const int64_t out0 = kWrite ? (int64_t)pos[a] : 0;
         int taken = 0;
-        for (uint32_t j0 = a + 1; j0 < end && taken < AID_FANOUT; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            bool ok = false, past = false;
-            int f2 = 0, dt = 0;
-            if (j < end) {
-                const uint32_t kb = peaks[j];
-                f2 = (int)(kb & (AID_NBINS - 1));
-                dt = (int)(kb >> AID_PEAK_F_BITS) - t1;
-                const int df = f2 > f1 ? f2 - f1 : f1 - f2;
-                past = dt > AID_DT_MAX;
-                ok = dt >= AID_DT_MIN && !past && df >= AID_DF_MIN && df <= AID_DF_MAX;
+        for (uint32_t j = a + 1; j < end && taken < AID_FANOUT; j++) {
+            const uint32_t kb = peaks[j];
+            const int dt = (int)(kb >> AID_PEAK_F_BITS) - t1;
+            if (dt > AID_DT_MAX) break;                                     // peaks are in (t, f) order: nothing later qualifies
+            const int f2 = (int)(kb & (AID_NBINS - 1));
+            const int df = f2 > f1 ? f2 - f1 : f1 - f2;
+            if (dt >= AID_DT_MIN && df >= AID_DF_MIN && df <= AID_DF_MAX) {
+                if (kWrite) {
+                    const int64_t o = out0 + taken;
+                    if (o < hash_cap) { hash[o] = AID_HASH(f1, f2, dt); t_anchor[o] = (uint32_t)t1; }
+                    else *overflow = 1;
+                }
+                taken++;
             }
-            const uint32_t bal = __ballot_sync(AID_FULL_MASK, ok);
-            const int rank = taken + __popc(bal & ((1u << lane) - 1));
-            if (kWrite && ok && rank < AID_FANOUT) {
-                const int64_t o = (int64_t)out0 + rank;
-                if (o < hash_cap) { hash[o] = AID_HASH(f1, f2, dt); t_anchor[o] = (uint32_t)t1; }
-                else *overflow = 1;
-            }
-            taken += __popc(bal);
-            if (__any_sync(AID_FULL_MASK, past)) break;
         }
-        if (!kWrite && lane == 0) cnt[a] = (uint32_t)min(taken, AID_FANOUT);
+        if (!kWrite) cnt[a] = (uint32_t)taken;
     }
 }
 
@@ -66,7 +61,7 @@ __global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* _
 }  // namespace
 
 static int hash_grid(int64_t max_peaks) {
-    int64_t need = (max_peaks + (kThreads / 32) - 1) / (kThreads / 32);
+    int64_t need = (max_peaks + kThreads - 1) / kThreads;
     const int64_t cap = 148 * 8;
     return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
